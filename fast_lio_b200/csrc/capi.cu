@@ -1,0 +1,193 @@
+// extern "C" boundary (include/fastlio_b200.h).  Thin: argument checks, handle plumbing,
+// status codes.  No torch types, no exceptions.
+#include <mutex>
+#include <new>
+
+#include "../../include/fastlio_b200.h"
+#include "filter.h"
+
+namespace fl {
+const char* last_error();
+int nccl_unique_id(void* out128);
+}  // namespace fl
+
+struct fl_map {
+    fl::Map* impl;
+    std::mutex mu;
+};
+struct fl_filter {
+    fl::Filter* impl;
+    fl_map* map;
+    fl::DeviceBuffer flush;
+    fl::DeviceBuffer ctl0;
+};
+
+static_assert(sizeof(fl_pass_log_t) == sizeof(fl::PassLog), "pass-log layouts must match");
+
+extern "C" {
+
+const char* fl_last_error(void) { return fl::last_error(); }
+int fl_version(void) { return 100; }
+int fl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------ map
+int fl_map_create(fl_map_t** out, int device, float downsample_size) {
+    if (!out) { fl::set_last_error("fl_map_create: null out"); return FL_ERR_ARG; }
+    *out = nullptr;
+    int n = fl_device_count();
+    if (n <= 0) { fl::set_last_error("fl_map_create: no CUDA device visible (this library has no CPU path)"); return FL_ERR_CUDA; }
+    if (device < 0 || device >= n) { fl::set_last_error("fl_map_create: device %d out of range [0, %d)", device, n); return FL_ERR_ARG; }
+    fl_map* m = new (std::nothrow) fl_map();
+    if (!m) return FL_ERR_CAPACITY;
+    m->impl = new (std::nothrow) fl::Map(device, downsample_size);
+    if (!m->impl) { delete m; return FL_ERR_CAPACITY; }
+    int rc = m->impl->init();
+    if (rc != FL_OK) { delete m->impl; delete m; return rc; }
+    *out = m;
+    return FL_OK;
+}
+int fl_map_destroy(fl_map_t* m) {
+    if (!m) return FL_OK;
+    delete m->impl;
+    delete m;
+    return FL_OK;
+}
+#define MAP_GUARD(m)                                                             \
+    if (!(m) || !(m)->impl) { fl::set_last_error("null map handle"); return FL_ERR_ARG; } \
+    std::lock_guard<std::mutex> _lk((m)->mu)
+
+int fl_map_set_downsample(fl_map_t* m, float v) { MAP_GUARD(m); m->impl->set_downsample(v); return FL_OK; }
+int fl_map_build(fl_map_t* m, const float* pts, int n) { MAP_GUARD(m); return m->impl->build(pts, n); }
+int fl_map_size(fl_map_t* m) { MAP_GUARD(m); return m->impl->size(); }
+int fl_map_validnum(fl_map_t* m) { MAP_GUARD(m); return m->impl->validnum(); }
+int fl_map_knn(fl_map_t* m, const float* q, int nq, int k, float* out_pts, float* out_d2, int* out_cnt) {
+    MAP_GUARD(m);
+    if (nq > 0 && (!q || !out_pts || !out_d2 || !out_cnt)) { fl::set_last_error("fl_map_knn: null buffer"); return FL_ERR_ARG; }
+    return m->impl->knn(q, nq, k, out_pts, out_d2, out_cnt);
+}
+int fl_map_add_points(fl_map_t* m, const float* pts, int n, int downsample_on) {
+    MAP_GUARD(m);
+    int added = 0;
+    int rc = m->impl->add_points(pts, n, downsample_on != 0, &added);
+    return rc == FL_OK ? added : rc;
+}
+int fl_map_delete_boxes(fl_map_t* m, const float* boxes6, int nb) {
+    MAP_GUARD(m);
+    int deleted = 0;
+    int rc = m->impl->delete_boxes(boxes6, nb, &deleted);
+    return rc == FL_OK ? deleted : rc;
+}
+int fl_map_flatten(fl_map_t* m, float* out, int cap) {
+    MAP_GUARD(m);
+    int n = 0;
+    int rc = m->impl->flatten(out, cap, &n);
+    return rc == FL_OK ? n : rc;
+}
+int fl_map_tree_range(fl_map_t* m, float* box6) { MAP_GUARD(m); if (!box6) return FL_ERR_ARG; return m->impl->tree_range(box6); }
+int fl_map_rebuild(fl_map_t* m) { MAP_GUARD(m); return m->impl->rebuild(); }
+int fl_map_stats(fl_map_t* m, int* out4) {
+    MAP_GUARD(m);
+    if (!out4) return FL_ERR_ARG;
+    out4[0] = m->impl->view().n_main; out4[1] = m->impl->overflow_leaves();
+    out4[2] = m->impl->view().n_levels; out4[3] = m->impl->rebuild_count();
+    return FL_OK;
+}
+
+// ------------------------------------------------------------------------------------ filter
+#define FILTER_GUARD(f)                                                                        \
+    if (!(f) || !(f)->impl) { fl::set_last_error("null filter handle"); return FL_ERR_ARG; }   \
+    std::lock_guard<std::mutex> _lk((f)->map->mu)
+
+int fl_filter_create(fl_filter_t** out, fl_map_t* map, int max_points) {
+    if (!out || !map || !map->impl) { fl::set_last_error("fl_filter_create: null argument"); return FL_ERR_ARG; }
+    *out = nullptr;
+    fl_filter* f = new (std::nothrow) fl_filter();
+    if (!f) return FL_ERR_CAPACITY;
+    f->map = map;
+    f->impl = new (std::nothrow) fl::Filter(map->impl, max_points);
+    if (!f->impl) { delete f; return FL_ERR_CAPACITY; }
+    int rc = f->impl->init();
+    if (rc != FL_OK) { delete f->impl; delete f; return rc; }
+    *out = f;
+    return FL_OK;
+}
+int fl_filter_destroy(fl_filter_t* f) {
+    if (!f) return FL_OK;
+    f->flush.release(); f->ctl0.release();
+    delete f->impl;
+    delete f;
+    return FL_OK;
+}
+int fl_filter_set_params(fl_filter_t* f, int max_iter, const double* limit23, int extr) { FILTER_GUARD(f); return f->impl->set_params(max_iter, limit23, extr); }
+int fl_filter_set_solver(fl_filter_t* f, int mode) { FILTER_GUARD(f); if (mode < 0 || mode > 1) return FL_ERR_ARG; f->impl->set_solver(mode); return FL_OK; }
+int fl_filter_update(fl_filter_t* f, const float* body, int nq, double* x26, double* P, double R, double* solve_time_s) {
+    FILTER_GUARD(f);
+    return f->impl->update(body, nq, x26, P, R, solve_time_s);
+}
+int fl_filter_get_nearest(fl_filter_t* f, float* out_pts, int* out_cnt, int nq) { FILTER_GUARD(f); return f->impl->get_nearest(out_pts, out_cnt, nq); }
+int fl_filter_get_selected(fl_filter_t* f, unsigned char* out, int nq) { FILTER_GUARD(f); if (!out) return FL_ERR_ARG; return f->impl->get_selected(out, nq); }
+int fl_filter_get_pass_logs(fl_filter_t* f, fl_pass_log_t* out, int cap) {
+    FILTER_GUARD(f);
+    if (!out || cap < 0) return FL_ERR_ARG;
+    int n = 0;
+    int rc = f->impl->get_pass_logs(reinterpret_cast<fl::PassLog*>(out), cap, &n);
+    return rc == FL_OK ? n : rc;
+}
+int fl_filter_upload_scan(fl_filter_t* f, const float* body, int nq) { FILTER_GUARD(f); return f->impl->upload_scan(body, nq); }
+int fl_filter_upload_state(fl_filter_t* f, const double* x26, const double* P, double R) {
+    FILTER_GUARD(f);
+    if (!x26 || !P) return FL_ERR_ARG;
+    return f->impl->upload_state(x26, P, R);
+}
+int fl_filter_run(fl_filter_t* f) { FILTER_GUARD(f); return f->impl->run_passes(); }
+int fl_filter_download_state(fl_filter_t* f, double* x26, double* P, int* n_pass) { FILTER_GUARD(f); return f->impl->download_state(x26, P, n_pass); }
+int fl_filter_sync(fl_filter_t* f) { FILTER_GUARD(f); return f->impl->sync(); }
+int fl_filter_gpu_launches(fl_filter_t* f) { FILTER_GUARD(f); return f->impl->gpu_launches(); }
+
+int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_total) {
+    FILTER_GUARD(f);
+    if (reps < 1 || !ms_total) return FL_ERR_ARG;
+    fl::Filter* F = f->impl;
+    cudaStream_t st = F->stream();
+    FL_CUDA(cudaSetDevice(F->map()->device()));
+    const size_t ctl_bytes = offsetof(fl::FilterCtl, P_prop);
+    FL_CHECK(f->ctl0.reserve(ctl_bytes));
+    FL_CUDA(cudaMemcpyAsync(f->ctl0.ptr, F->ctl_device(), ctl_bytes, cudaMemcpyDeviceToDevice, st));
+    const size_t flush_bytes = 256u << 20;       // > 126 MB of L2
+    if (flush_l2) FL_CHECK(f->flush.reserve(flush_bytes));
+    cudaEvent_t e0, e1;
+    FL_CUDA(cudaEventCreate(&e0));
+    FL_CUDA(cudaEventCreate(&e1));
+    float total = 0.f;
+    for (int r = 0; r < reps; r++) {
+        FL_CUDA(cudaMemcpyAsync((void*)F->ctl_device(), f->ctl0.ptr, ctl_bytes, cudaMemcpyDeviceToDevice, st));
+        if (flush_l2) FL_CUDA(cudaMemsetAsync(f->flush.ptr, r & 0xff, flush_bytes, st));
+        FL_CUDA(cudaEventRecord(e0, st));
+        int rc = F->run_passes();
+        if (rc != FL_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+        FL_CUDA(cudaEventRecord(e1, st));
+        FL_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        FL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_total = total;
+    return FL_OK;
+}
+
+// ------------------------------------------------------------------------------------ multi-GPU
+int fl_comm_unique_id(void* out128) { if (!out128) return FL_ERR_ARG; return fl::nccl_unique_id(out128); }
+int fl_filter_comm_init(fl_filter_t* f, int nranks, int rank, const void* id128) {
+    FILTER_GUARD(f);
+    if (nranks > 1 && !id128) return FL_ERR_ARG;
+    return f->impl->comm_init(nranks, rank, id128);
+}
+int fl_filter_set_shard(fl_filter_t* f, int q_begin, int q_end) { FILTER_GUARD(f); return f->impl->set_shard(q_begin, q_end); }
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// Host-side owner of the per-scan iterated-EKF measurement update on the device: the B200
+// counterpart of esekfom::esekf<state_ikfom,12,input_ikfom>::update_iterated_dyn_share_modified
+// (reference include/IKFoM_toolkit/esekfom/esekfom.hpp:1619-1931) with h_share_model
+// (reference src/laserMapping.cpp:638-754) bound as a fused device measurement model.
+#pragma once
+#include "lie.cuh"
+#include "map.h"
+
+namespace fl {
+
+// Per-pass record, same layout as the oracle's OraclePassLog (tests compare them field by field).
+struct PassLog {
+    int searched, valid, effct, converged;
+    double res_sum;
+    double HtH[144];
+    double Hth[12];
+    double x_after[XLEN];
+};
+
+// Device-resident control block of one update (what the reference keeps in locals of
+// update_iterated_dyn_share_modified and in members x_, P_ of esekf).
+struct FilterCtl {
+    int iter;            // loop variable i, starts at -1            (esekfom.hpp:1633)
+    int t;               // converged-step counter                   (esekfom.hpp:1624)
+    int converge;        // dyn_share.converge: run the kNN on the next pass
+    int done;            // the update has returned
+    int n_pass;          // passes executed so far
+    int max_iter;        // maximum_iter
+    int extrinsic_est;   // extrinsic_est_en (laserMapping.cpp:739)
+    int error;           // device-side failure (singular system)
+    double R;            // LASER_POINT_COV passed as R
+    double limit[NDOF];
+    double x[XLEN];
+    double x_prop[XLEN];
+    double P[NDOF * NDOF];
+    double P_prop[NDOF * NDOF];
+};
+
+struct ScanView {
+    const float4* body;      // [Q] body-frame points (x, y, z, intensity)      feats_down_body
+    float4* nearest;         // [Q * 5] neighbours of the last search pass      Nearest_Points
+    int* nearest_cnt;        // [Q]
+    unsigned char* selected; // [Q] point_selected_surf (persists across passes, trap T3)
+    float4* normvec;         // [Q] (n, pd2)                                    normvec
+    int q_begin, q_end;      // this rank's shard of the scan
+    int Q;
+};
+
+struct NcclApi;
+
+class Filter {
+public:
+    Filter(Map* map, int max_points);
+    ~Filter();
+    int init();
+    int set_params(int max_iter, const double* limit23, int extrinsic_est_en);
+    void set_solver(int mode) { solver_ = mode; }       // 0: reference-mirroring two 23x23 inverses; 1: 12x12 Woodbury form
+
+    // whole update with host buffers (scan H2D, state H2D, passes, state D2H)
+    int update(const float* body_xyzi, int nq, double* x26, double* P, double R, double* solve_time_s);
+    // pieces, for device-resident benchmarking / pipelines
+    int upload_scan(const float* body_xyzi, int nq);
+    int set_scan_device(const float4* d_body, int nq);
+    int upload_state(const double* x26, const double* P, double R);
+    int run_passes();                                  // enqueue every pass on the stream (no sync)
+    int download_state(double* x26, double* P, int* n_pass);
+    int sync();
+
+    int get_nearest(float* out_pts, int* out_cnt, int nq);
+    int get_selected(unsigned char* out, int nq);
+    int get_pass_logs(PassLog* out, int cap, int* n);
+    // multi-GPU: scan points sharded across ranks, map replicated, one all-reduce per pass
+    int comm_init(int nranks, int rank, const void* nccl_unique_id_128);
+    int set_shard(int q_begin, int q_end);             // default: the whole scan
+
+    int gpu_launches() const { return launches_; }
+    const float4* nearest_device() const { return scan_.nearest; }
+    const ScanView& scan() const { return scan_; }
+    cudaStream_t stream() const { return map_->stream(); }
+    Map* map() const { return map_; }
+    const FilterCtl* ctl_device() const { return ctl_.as<FilterCtl>(); }
+
+private:
+    int reserve(int nq);
+    Map* map_;
+    int max_points_;
+    int max_iter_ = 4;
+    double limit_[NDOF];
+    int extrinsic_est_ = 0;
+    int solver_ = 0;
+    ScanView scan_;
+    DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, partials_, red_, ctl_, logs_;
+    FilterCtl* h_ctl_ = nullptr;       // pinned staging
+    int grid_ = 0;
+    int launches_ = 0;
+    bool shard_set_ = false;
+    // NCCL (resolved lazily with dlopen so that single-GPU use needs no NCCL at all)
+    NcclApi* nccl_ = nullptr;
+    void* comm_ = nullptr;
+    int nranks_ = 1, rank_ = 0;
+};
+
+}  // namespace fl

@@ -1,0 +1,685 @@
+// Device point map: build / refit / search / box-delete / incremental insert.
+// B200-native replacement for the subset of KD_TREE<PointType> that FAST-LIO's
+// laserMapping.cpp calls (reference include/ikd-Tree/ikd_Tree.cpp).  See map.cuh for the
+// memory layout and DESIGN.md for the rationale.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdarg>
+#include <vector>
+
+#include "map.h"
+
+namespace fl {
+
+// ============================================================================= errors
+static thread_local char g_last_error[512] = "";
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_last_error; }
+
+// ============================================================================= DeviceBuffer
+int DeviceBuffer::reserve(size_t want) {
+    if (want <= bytes) return FL_OK;
+    size_t grow = std::max(want, bytes + bytes / 2);
+    if (ptr) { FL_CUDA(cudaFree(ptr)); ptr = nullptr; bytes = 0; }
+    FL_CUDA(cudaMalloc(&ptr, grow));
+    bytes = grow;
+    return FL_OK;
+}
+void DeviceBuffer::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; bytes = 0;
+}
+
+// counters_ layout
+enum Counter { C_LEAF_USED = 0, C_DELETED, C_ADDED, C_GROUPS, C_NINSERT, C_TOMB, C_ERROR, C_COMPACT, C_COUNT = 16 };
+
+// ============================================================================= kernels
+__global__ void k_morton_keys(const float4* __restrict__ src, int n, unsigned long long* __restrict__ keys,
+                              unsigned* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float4 p = src[i];
+        keys[i] = morton_key(p.x, p.y, p.z);
+        vals[i] = (unsigned)i;
+    }
+}
+
+// Scatter the Morton-sorted points into leaf buckets (`fill` points per leaf), clear the
+// remaining slots and the whole overflow pool, reset the chains.
+__global__ void k_fill_leaves(MapView m, const float4* __restrict__ src, const unsigned long long* __restrict__ keys,
+                              const unsigned* __restrict__ vals, int n, int fill) {
+    const long long total = (long long)m.leaf_cap * LEAF;
+    for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < total;
+         slot += (long long)gridDim.x * blockDim.x) {
+        const int leaf = (int)(slot / LEAF), s = (int)(slot % LEAF);
+        float4 out = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        float pay = 0.f;
+        if (leaf < m.n_main && s < fill) {
+            const long long r = (long long)leaf * fill + s;
+            if (r < n) {
+                const float4 p = src[vals[r]];
+                out = make_float4(p.x, p.y, p.z, __int_as_float(1));
+                pay = p.w;
+            }
+        }
+        m.pts[slot] = out;
+        m.payload[slot] = pay;
+        if (s == 0) {
+            m.next[leaf] = -1;
+            if (leaf < m.n_main) {
+                const long long r0 = (long long)leaf * fill;
+                m.esep[0][leaf] = (leaf == 0 || r0 >= n) ? (leaf == 0 ? 0ull : ~0ull) : keys[r0];
+            }
+        }
+    }
+}
+
+// One warp per main leaf: AABB of the valid points of the leaf and of its overflow chain.
+__global__ void k_refit_leaves(MapView m) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; leaf < m.n_main; leaf += warps) {
+        float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+        int l = leaf;
+        while (l >= 0) {
+            const float4 p = m.pts[l * LEAF + lane];
+            if (slot_valid(p)) {
+                lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z);
+                hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z);
+            }
+            l = m.next[l];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(FULL, lx, o)); ly = fminf(ly, __shfl_xor_sync(FULL, ly, o));
+            lz = fminf(lz, __shfl_xor_sync(FULL, lz, o)); hx = fmaxf(hx, __shfl_xor_sync(FULL, hx, o));
+            hy = fmaxf(hy, __shfl_xor_sync(FULL, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(FULL, hz, o));
+        }
+        if (lane == 0) {
+            m.ebox[0][2 * leaf] = make_float4(lx, ly, lz, 0.f);
+            m.ebox[0][2 * leaf + 1] = make_float4(hx, hy, hz, 0.f);
+        }
+    }
+}
+
+// One warp per entity of level k (k >= 1): union of its <= 32 children boxes, first child's separator.
+__global__ void k_refit_level(MapView m, int k) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < m.count[k]; e += warps) {
+        const int c = e * FAN + lane;
+        float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+        if (c < m.count[k - 1]) {
+            const float4 lo = m.ebox[k - 1][2 * c], hi = m.ebox[k - 1][2 * c + 1];
+            lx = lo.x; ly = lo.y; lz = lo.z; hx = hi.x; hy = hi.y; hz = hi.z;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(FULL, lx, o)); ly = fminf(ly, __shfl_xor_sync(FULL, ly, o));
+            lz = fminf(lz, __shfl_xor_sync(FULL, lz, o)); hx = fmaxf(hx, __shfl_xor_sync(FULL, hx, o));
+            hy = fmaxf(hy, __shfl_xor_sync(FULL, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(FULL, hz, o));
+        }
+        if (lane == 0) {
+            m.ebox[k][2 * e] = make_float4(lx, ly, lz, 0.f);
+            m.ebox[k][2 * e + 1] = make_float4(hx, hy, hz, 0.f);
+            m.esep[k][e] = m.esep[k - 1][e * FAN];
+        }
+    }
+}
+
+// Batched Nearest_Search: one warp per query.
+__global__ void __launch_bounds__(256) k_knn_batch(MapView m, const float4* __restrict__ q, int nq, int k,
+                                                    float4* __restrict__ out_pts, float* __restrict__ out_d2,
+                                                    int* __restrict__ out_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += warps) {
+        const float4 qq = __ldg(&q[i]);
+        KBest kb;
+        knn_query(m, qq.x, qq.y, qq.z, kb, lane);
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < KNN_K; j++) cnt += (kb.idx[j] >= 0 && j < k) ? 1 : 0;
+        // lane j fetches neighbour j
+        int myidx = -1; float myd = INFINITY;
+#pragma unroll
+        for (int j = 0; j < KNN_K; j++) if (lane == j) { myidx = kb.idx[j]; myd = kb.d[j]; }
+        if (lane < k) {
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (myidx >= 0) { p = m.pts[myidx]; p.w = m.payload[myidx]; }
+            out_pts[(size_t)i * k + lane] = p;
+            out_d2[(size_t)i * k + lane] = myd;
+        }
+        if (lane == 0) out_cnt[i] = cnt;
+    }
+}
+
+// Delete_Point_Boxes: every slot tests itself against the boxes (half-open, ikd_Tree.cpp:796).
+// A flat pass over the leaf array is bandwidth-trivial on HBM3e (16 B per slot) and needs
+// no tree descent, no lazy flags and no push-down.
+__global__ void k_delete_boxes(MapView m, const float* __restrict__ boxes, int nb, int n_leaf_used, int* counters) {
+    const long long total = (long long)n_leaf_used * LEAF;
+    int local = 0;
+    for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < total;
+         slot += (long long)gridDim.x * blockDim.x) {
+        float4 p = m.pts[slot];
+        if (slot_valid(p)) {
+            bool hit = false;
+            for (int b = 0; b < nb && !hit; b++) hit = in_box(p, &boxes[b * 6], &boxes[b * 6 + 3]);
+            if (hit) { m.pts[slot].w = __int_as_float(0); local++; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counters[C_DELETED], local);
+}
+
+// Compaction of every valid point (x, y, z, intensity) -- flatten() and the input of rebuild().
+__global__ void k_compact(MapView m, int n_leaf_used, float4* __restrict__ out, int* counters) {
+    const long long total = (long long)n_leaf_used * LEAF;
+    const int lane = threadIdx.x & 31;
+    for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < total;
+         base += (long long)gridDim.x * blockDim.x) {
+        const long long slot = base + lane;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool v = false;
+        if (slot < total) { p = m.pts[slot]; v = slot_valid(p); }
+        const unsigned mask = __ballot_sync(FULL, v);
+        int off = 0;
+        if (lane == 0 && mask) off = atomicAdd(&counters[C_COMPACT], __popc(mask));
+        off = __shfl_sync(FULL, off, 0);
+        if (v) {
+            p.w = m.payload[slot];
+            out[off + __popc(mask & ((1u << lane) - 1))] = p;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- Add_Points
+// Voxel of a point exactly as Add_Points computes it (ikd_Tree.cpp:491-499): float division,
+// float floor, float multiply.
+struct VoxelBox { float bmin[3], bmax[3], mid[3]; };
+__device__ __forceinline__ void voxel_box(const float4& p, float ds, VoxelBox& vb) {
+    const float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        vb.bmin[a] = __fmul_rn(floorf(__fdiv_rn(c[a], ds)), ds);
+        vb.bmax[a] = __fadd_rn(vb.bmin[a], ds);
+        // mid = min + (max - min) / 2.0  evaluated in double, stored to float (ikd_Tree.cpp:497-499)
+        vb.mid[a] = (float)((double)vb.bmin[a] + (double)__fsub_rn(vb.bmax[a], vb.bmin[a]) / 2.0);
+    }
+}
+__device__ __forceinline__ unsigned long long voxel_key(const float4& p, float ds) {
+    unsigned long long key = 0;
+    const float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float f = floorf(__fdiv_rn(c[a], ds)) + 1048576.0f;
+        f = f < 0.f ? 0.f : (f > 2097151.f ? 2097151.f : f);
+        key = (key << 21) | (unsigned long long)(unsigned)f;
+    }
+    return key;
+}
+__global__ void k_voxel_keys(const float4* __restrict__ pts, int n, float ds, unsigned long long* __restrict__ keys,
+                             unsigned* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = voxel_key(pts[i], ds); vals[i] = (unsigned)i; }
+}
+__global__ void k_group_heads(const unsigned long long* __restrict__ keys, int n, int* __restrict__ group_start, int* counters) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n && (r == 0 || keys[r] != keys[r - 1])) group_start[atomicAdd(&counters[C_GROUPS], 1)] = r;
+}
+
+struct BoxScan {       // pass 1: count the valid points inside the voxel and find the one closest to its centre
+    const MapView& m; const VoxelBox& vb; int lane;
+    int count = 0; float best_d = INFINITY; int best_slot = -1;
+    __device__ BoxScan(const MapView& m_, const VoxelBox& vb_, int lane_) : m(m_), vb(vb_), lane(lane_) {}
+    __device__ __forceinline__ void leaf(int l) {
+        while (l >= 0) {
+            const int slot = l * LEAF + lane;
+            const float4 p = m.pts[slot];
+            const bool in = slot_valid(p) && in_box(p, vb.bmin, vb.bmax);
+            const unsigned mask = __ballot_sync(FULL, in);
+            if (mask) {
+                count += __popc(mask);
+                const float d = in ? sq_dist3(p.x, p.y, p.z, vb.mid[0], vb.mid[1], vb.mid[2]) : INFINITY;
+                const unsigned key = in ? __float_as_uint(d) : 0xffffffffu;
+                const unsigned best = __reduce_min_sync(FULL, key);
+                if (__uint_as_float(best) < best_d) {       // strict: the first one found wins ties (ikd_Tree.cpp:508)
+                    best_d = __uint_as_float(best);
+                    best_slot = l * LEAF + (__ffs(__ballot_sync(FULL, key == best)) - 1);
+                }
+            }
+            l = m.next[l];
+        }
+    }
+};
+struct BoxKill {       // pass 2: invalidate every valid point inside the voxel except `keep`
+    const MapView& m; const VoxelBox& vb; int lane; int keep;
+    __device__ BoxKill(const MapView& m_, const VoxelBox& vb_, int lane_, int keep_) : m(m_), vb(vb_), lane(lane_), keep(keep_) {}
+    __device__ __forceinline__ void leaf(int l) {
+        while (l >= 0) {
+            const int slot = l * LEAF + lane;
+            const float4 p = m.pts[slot];
+            if (slot_valid(p) && in_box(p, vb.bmin, vb.bmax) && slot != keep) m.pts[slot].w = __int_as_float(0);
+            l = m.next[l];
+        }
+    }
+};
+
+__device__ __forceinline__ bool same_point(const float4& a, const float4& b) {   // ikd_Tree.cpp:1676-1680, EPSS = 1e-6
+    return fabs((double)a.x - (double)b.x) < 1e-6 && fabs((double)a.y - (double)b.y) < 1e-6 && fabs((double)a.z - (double)b.z) < 1e-6;
+}
+
+// One warp per touched voxel.  Reproduces the sequential per-point semantics of
+// Add_Points(downsample_on = true) (ikd_Tree.cpp:489-521) for all batch points that fall
+// into the voxel, in their original order (the sort is stable).
+__global__ void __launch_bounds__(256) k_downsample_resolve(MapView m, const float4* __restrict__ batch,
+                                                             const unsigned long long* __restrict__ keys,
+                                                             const unsigned* __restrict__ vals, int n,
+                                                             const int* __restrict__ group_start, float ds,
+                                                             float4* __restrict__ insert_list, int* counters) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_groups = counters[C_GROUPS];
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+        const int r0 = group_start[g];
+        const unsigned long long key = keys[r0];
+        const float4 first = batch[vals[r0]];
+        VoxelBox vb;
+        voxel_box(first, ds, vb);
+        BoxScan scan(m, vb, lane);
+        box_query(m, vb.bmin, vb.bmax, scan, lane);
+        // ---- sequential resolution (warp-uniform scalar work)
+        int cur_count = scan.count;
+        float cur_d = scan.best_d;
+        int cur_slot = scan.best_slot;        // >= 0: existing map point; -1: none / a batch point
+        int cur_batch = -1;                   // index into batch[] if the current best is a new point
+        float4 cur_pt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cur_slot >= 0) cur_pt = m.pts[cur_slot];
+        bool modified = false;
+        int added = 0;
+        for (int r = r0; r < n && keys[r] == key; r++) {
+            const int bi = (int)vals[r];
+            const float4 p = batch[bi];
+            const float d_new = sq_dist3(p.x, p.y, p.z, vb.mid[0], vb.mid[1], vb.mid[2]);
+            const bool cur_wins = cur_count > 0 && cur_d < d_new;       // tmp_dist < min_dist
+            const bool same = !cur_wins || same_point(p, cur_pt);
+            if (cur_count > 1 || same) {
+                modified = true;
+                added++;
+                if (!cur_wins) { cur_d = d_new; cur_slot = -1; cur_batch = bi; cur_pt = p; }
+                cur_count = 1;
+            }
+        }
+        if (modified) {
+            const int keep = cur_slot;            // existing survivor stays in place (== delete + re-add of the same point)
+            BoxKill kill(m, vb, lane, keep);
+            box_query(m, vb.bmin, vb.bmax, kill, lane);
+            if (lane == 0) {
+                const int killed = scan.count - (keep >= 0 ? 1 : 0);
+                if (killed) atomicAdd(&counters[C_TOMB], killed);
+                if (keep < 0) insert_list[atomicAdd(&counters[C_NINSERT], 1)] = batch[cur_batch];
+                atomicAdd(&counters[C_ADDED], added);
+            }
+        }
+    }
+}
+
+// One warp per new point: descend the separators to the home leaf, claim a free slot there or
+// in its overflow chain (allocating a chain leaf from the pool if needed), publish the point
+// and grow the AABBs on the root path with float atomics ("partial refit").
+__global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restrict__ pts, int n, int* counters) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const float4 p = pts[i];
+        const unsigned long long key = morton_key(p.x, p.y, p.z);
+        int node = 0;
+        for (int k = m.n_levels - 1; k >= 0; k--) {
+            const int e = node * FAN + lane;
+            const unsigned long long sep = (e < m.count[k]) ? m.esep[k][e] : ~0ull;
+            const unsigned mask = __ballot_sync(FULL, sep <= key);
+            const int c = mask ? (__popc(mask) - 1) : 0;
+            node = node * FAN + c;
+        }
+        const int home = node;
+        int leaf = home;
+        bool placed = false;
+        while (!placed) {
+            const int w = __float_as_int(m.pts[leaf * LEAF + lane].w);
+            unsigned freem = __ballot_sync(FULL, w == 0);
+            while (freem && !placed) {
+                const int s = __ffs(freem) - 1;
+                int old = 0;
+                if (lane == 0) old = atomicCAS((int*)&m.pts[leaf * LEAF + s].w, 0, 2);
+                old = __shfl_sync(FULL, old, 0);
+                if (old == 0) {
+                    if (lane == 0) {
+                        m.payload[leaf * LEAF + s] = p.w;
+                        m.pts[leaf * LEAF + s] = make_float4(p.x, p.y, p.z, __int_as_float(1));
+                    }
+                    placed = true;
+                } else {
+                    freem &= ~(1u << s);
+                }
+            }
+            if (placed) break;
+            int nxt = 0;
+            if (lane == 0) {
+                nxt = atomicAdd(&m.next[leaf], 0);
+                if (nxt < 0) {
+                    int fresh = atomicAdd(&counters[C_LEAF_USED], 1);
+                    if (fresh >= m.leaf_cap) { atomicExch(&counters[C_ERROR], 1); nxt = -2; }
+                    else {
+                        int old = atomicCAS(&m.next[leaf], -1, fresh);
+                        nxt = (old == -1) ? fresh : old;       // lost the race: follow the winner (the fresh leaf stays unused)
+                    }
+                }
+            }
+            nxt = __shfl_sync(FULL, nxt, 0);
+            if (nxt < 0) break;                                    // pool exhausted (host guarantees this cannot happen)
+            leaf = nxt;
+        }
+        if (!placed) continue;
+        // grow the boxes of the home leaf and of its ancestors
+        int e = home;
+        const float c3[3] = {p.x, p.y, p.z};
+        for (int k = 0; k < m.n_levels; k++) {
+            if (lane < 3) atomic_min_float(&((float*)&m.ebox[k][2 * e])[lane], c3[lane]);
+            else if (lane < 6) atomic_max_float(&((float*)&m.ebox[k][2 * e + 1])[lane - 3], c3[lane - 3]);
+            e /= FAN;
+        }
+    }
+}
+
+// ============================================================================= host
+static inline int blocks_for(long long threads, int block, int cap = 148 * 16) {
+    long long b = (threads + block - 1) / block;
+    return (int)std::max<long long>(1, std::min<long long>(b, cap));
+}
+
+Map::Map(int device, float downsample_size) : device_(device), downsample_(downsample_size) { memset(&v_, 0, sizeof(v_)); }
+
+Map::~Map() {
+    cudaSetDevice(device_);
+    pts_.release(); payload_.release(); next_.release(); counters_.release();
+    for (int k = 0; k < MAX_LEVELS; k++) { ebox_[k].release(); esep_[k].release(); }
+    src_.release(); keys_in_.release(); keys_out_.release(); vals_in_.release(); vals_out_.release();
+    cub_tmp_.release(); scratch_.release(); scratch2_.release(); scratch3_.release();
+    if (h_counters_) cudaFreeHost(h_counters_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+int Map::init() {
+    FL_CUDA(cudaSetDevice(device_));
+    FL_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    FL_CHECK(counters_.reserve(sizeof(int) * C_COUNT));
+    FL_CUDA(cudaMemsetAsync(counters_.ptr, 0, sizeof(int) * C_COUNT, stream_));
+    FL_CUDA(cudaMallocHost(&h_counters_, sizeof(int) * C_COUNT));
+    v_.n_leaf_used = counters_.as<int>();
+    // an empty map: one empty leaf under a one-level root, so that every kernel is well defined
+    FL_CHECK(src_.reserve(sizeof(float4)));
+    return build_from_sorted(src_.as<float4>(), 0);
+}
+
+int Map::ensure_capacity(int n_points) {
+    const int n_main = std::max(1, (n_points + fill_ - 1) / fill_);
+    // overflow pool: half the main leaves, never less than 64k leaves (32 MB) -- enough for
+    // any single Add_Points batch to take one fresh leaf per point in the worst case
+    const long long want = (long long)n_main + std::max<long long>(n_main / 2, min_pool_);
+    if (want > 0x7fffffff / LEAF) { set_last_error("map too large: %d points", n_points); return FL_ERR_CAPACITY; }
+    if (want > v_.leaf_cap || !pts_.ptr) {
+        FL_CHECK(pts_.reserve(sizeof(float4) * LEAF * (size_t)want));
+        FL_CHECK(payload_.reserve(sizeof(float) * LEAF * (size_t)want));
+        FL_CHECK(next_.reserve(sizeof(int) * (size_t)want));
+        v_.leaf_cap = (int)std::min<size_t>({pts_.bytes / (sizeof(float4) * LEAF), payload_.bytes / (sizeof(float) * LEAF),
+                                              next_.bytes / sizeof(int)});
+        v_.pts = pts_.as<float4>(); v_.payload = payload_.as<float>(); v_.next = next_.as<int>();
+    }
+    // level geometry
+    v_.n_main = n_main;
+    v_.count[0] = n_main;
+    int k = 0;
+    while (true) {
+        const int c = v_.count[k];
+        FL_CHECK(ebox_[k].reserve(sizeof(float4) * 2 * (size_t)c));
+        FL_CHECK(esep_[k].reserve(sizeof(unsigned long long) * (size_t)c));
+        v_.ebox[k] = ebox_[k].as<float4>();
+        v_.esep[k] = esep_[k].as<unsigned long long>();
+        const int up = (c + FAN - 1) / FAN;
+        k++;
+        v_.count[k] = up;
+        if (up == 1) break;
+        if (k >= MAX_LEVELS) { set_last_error("too many tree levels"); return FL_ERR_CAPACITY; }
+    }
+    v_.n_levels = k;
+    return FL_OK;
+}
+
+int Map::refit() {
+    FL_CUDA(cudaSetDevice(device_));
+    k_refit_leaves<<<blocks_for((long long)v_.n_main * 32, 256), 256, 0, stream_>>>(v_);
+    for (int k = 1; k < v_.n_levels; k++)
+        k_refit_level<<<blocks_for((long long)v_.count[k] * 32, 256), 256, 0, stream_>>>(v_, k);
+    FL_CUDA(cudaGetLastError());
+    return FL_OK;
+}
+
+// d_src: n points (x, y, z, intensity) on the device, any order.
+int Map::build_from_sorted(const float4* d_src, int n) {
+    FL_CUDA(cudaSetDevice(device_));
+    FL_CHECK(ensure_capacity(n));
+    if (n > 0) {
+        FL_CHECK(keys_in_.reserve(sizeof(unsigned long long) * (size_t)n));
+        FL_CHECK(keys_out_.reserve(sizeof(unsigned long long) * (size_t)n));
+        FL_CHECK(vals_in_.reserve(sizeof(unsigned) * (size_t)n));
+        FL_CHECK(vals_out_.reserve(sizeof(unsigned) * (size_t)n));
+        k_morton_keys<<<blocks_for(n, 256, 1 << 30), 256, 0, stream_>>>(d_src, n, keys_in_.as<unsigned long long>(), vals_in_.as<unsigned>());
+        size_t tmp = 0;
+        FL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in_.as<unsigned long long>(), keys_out_.as<unsigned long long>(),
+                                                vals_in_.as<unsigned>(), vals_out_.as<unsigned>(), n, 0, 63, stream_));
+        FL_CHECK(cub_tmp_.reserve(tmp));
+        tmp = cub_tmp_.bytes;
+        FL_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.ptr, tmp, keys_in_.as<unsigned long long>(), keys_out_.as<unsigned long long>(),
+                                                vals_in_.as<unsigned>(), vals_out_.as<unsigned>(), n, 0, 63, stream_));
+    }
+    k_fill_leaves<<<blocks_for((long long)v_.leaf_cap * LEAF, 256), 256, 0, stream_>>>(
+        v_, d_src, keys_out_.as<unsigned long long>(), vals_out_.as<unsigned>(), n, fill_);
+    FL_CUDA(cudaGetLastError());
+    h_counters_[C_LEAF_USED] = v_.n_main;
+    FL_CUDA(cudaMemcpyAsync(&counters_.as<int>()[C_LEAF_USED], &h_counters_[C_LEAF_USED], sizeof(int), cudaMemcpyHostToDevice, stream_));
+    FL_CHECK(refit());
+    FL_CUDA(cudaStreamSynchronize(stream_));
+    n_valid_ = n;
+    n_tomb_ = 0;
+    built_ = true;
+    return FL_OK;
+}
+
+int Map::build_device(const float4* d_pts_xyzi, int n) {
+    if (n < 0) { set_last_error("build: n < 0"); return FL_ERR_ARG; }
+    return build_from_sorted(d_pts_xyzi, n);
+}
+
+int Map::build(const float* pts_xyzi, int n) {
+    if (n < 0 || (n > 0 && !pts_xyzi)) { set_last_error("build: bad arguments"); return FL_ERR_ARG; }
+    FL_CUDA(cudaSetDevice(device_));
+    FL_CHECK(src_.reserve(sizeof(float4) * (size_t)std::max(n, 1)));
+    if (n > 0) FL_CUDA(cudaMemcpyAsync(src_.ptr, pts_xyzi, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+    return build_from_sorted(src_.as<float4>(), n);
+}
+
+int Map::knn(const float* q_xyzi, int nq, int k, float* out_pts, float* out_d2, int* out_cnt) {
+    if (nq < 0 || k < 1 || k > KNN_K) { set_last_error("knn: k must be in [1, %d]", KNN_K); return FL_ERR_ARG; }
+    if (nq == 0) return FL_OK;
+    FL_CUDA(cudaSetDevice(device_));
+    const size_t qb = sizeof(float4) * (size_t)nq, pb = sizeof(float4) * (size_t)nq * k, db = sizeof(float) * (size_t)nq * k, cb = sizeof(int) * (size_t)nq;
+    FL_CHECK(scratch_.reserve(qb + pb + db + cb));
+    char* base = scratch_.as<char>();
+    float4* d_q = (float4*)base; float4* d_p = (float4*)(base + qb); float* d_d = (float*)(base + qb + pb); int* d_c = (int*)(base + qb + pb + db);
+    FL_CUDA(cudaMemcpyAsync(d_q, q_xyzi, qb, cudaMemcpyHostToDevice, stream_));
+    k_knn_batch<<<blocks_for((long long)nq * 32, 256), 256, 0, stream_>>>(v_, d_q, nq, k, d_p, d_d, d_c);
+    FL_CUDA(cudaGetLastError());
+    FL_CUDA(cudaMemcpyAsync(out_pts, d_p, pb, cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaMemcpyAsync(out_d2, d_d, db, cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaMemcpyAsync(out_cnt, d_c, cb, cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaStreamSynchronize(stream_));
+    return FL_OK;
+}
+
+int Map::overflow_leaves() const { return h_counters_ ? h_counters_[C_LEAF_USED] - v_.n_main : 0; }
+
+int Map::delete_boxes(const float* boxes6, int nb, int* deleted) {
+    if (deleted) *deleted = 0;
+    if (nb < 0 || (nb > 0 && !boxes6)) { set_last_error("delete_boxes: bad arguments"); return FL_ERR_ARG; }
+    if (nb == 0) return FL_OK;
+    FL_CUDA(cudaSetDevice(device_));
+    FL_CHECK(scratch_.reserve(sizeof(float) * 6 * (size_t)nb));
+    FL_CUDA(cudaMemcpyAsync(scratch_.ptr, boxes6, sizeof(float) * 6 * (size_t)nb, cudaMemcpyHostToDevice, stream_));
+    FL_CUDA(cudaMemsetAsync(&counters_.as<int>()[C_DELETED], 0, sizeof(int), stream_));
+    const int used = h_counters_[C_LEAF_USED];
+    k_delete_boxes<<<blocks_for((long long)used * LEAF, 256), 256, 0, stream_>>>(v_, scratch_.as<float>(), nb, used, counters_.as<int>());
+    FL_CUDA(cudaGetLastError());
+    FL_CUDA(cudaMemcpyAsync(&h_counters_[C_DELETED], &counters_.as<int>()[C_DELETED], sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaStreamSynchronize(stream_));
+    const int d = h_counters_[C_DELETED];
+    if (d > 0) {
+        n_valid_ -= d; n_tomb_ += d;
+        FL_CHECK(refit());          // tighten every AABB ("box-delete by refit")
+        FL_CHECK(maybe_rebuild());
+    }
+    if (deleted) *deleted = d;
+    return FL_OK;
+}
+
+int Map::flatten(float* out_xyzi, int cap, int* n_out) {
+    FL_CUDA(cudaSetDevice(device_));
+    FL_CHECK(src_.reserve(sizeof(float4) * (size_t)std::max(1, n_valid_)));
+    FL_CUDA(cudaMemsetAsync(&counters_.as<int>()[C_COMPACT], 0, sizeof(int), stream_));
+    const int used = h_counters_[C_LEAF_USED];
+    k_compact<<<blocks_for((long long)used * LEAF, 256), 256, 0, stream_>>>(v_, used, src_.as<float4>(), counters_.as<int>());
+    FL_CUDA(cudaGetLastError());
+    FL_CUDA(cudaMemcpyAsync(&h_counters_[C_COMPACT], &counters_.as<int>()[C_COMPACT], sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaStreamSynchronize(stream_));
+    const int n = h_counters_[C_COMPACT];
+    if (n != n_valid_) { set_last_error("flatten: %d valid points on device, host expected %d", n, n_valid_); return FL_ERR_STATE; }
+    if (n_out) *n_out = n;
+    if (out_xyzi && cap > 0) {
+        FL_CUDA(cudaMemcpyAsync(out_xyzi, src_.ptr, sizeof(float4) * (size_t)std::min(n, cap), cudaMemcpyDeviceToHost, stream_));
+        FL_CUDA(cudaStreamSynchronize(stream_));
+    }
+    return FL_OK;
+}
+
+int Map::rebuild() {
+    FL_CUDA(cudaSetDevice(device_));
+    FL_CHECK(src_.reserve(sizeof(float4) * (size_t)std::max(1, n_valid_)));
+    FL_CUDA(cudaMemsetAsync(&counters_.as<int>()[C_COMPACT], 0, sizeof(int), stream_));
+    const int used = h_counters_[C_LEAF_USED];
+    k_compact<<<blocks_for((long long)used * LEAF, 256), 256, 0, stream_>>>(v_, used, src_.as<float4>(), counters_.as<int>());
+    FL_CUDA(cudaGetLastError());
+    n_rebuilds_++;
+    return build_from_sorted(src_.as<float4>(), n_valid_);
+}
+
+int Map::maybe_rebuild() {
+    const int overflow = h_counters_[C_LEAF_USED] - v_.n_main;
+    const bool too_chained = overflow > std::max(64, (int)(rebuild_overflow_frac_ * v_.n_main));
+    const bool too_sparse = n_tomb_ > 1024 && n_tomb_ > n_valid_;       // ikd-Tree's delete criterion (alpha_del = 0.5)
+    if (too_chained || too_sparse) return rebuild();
+    return FL_OK;
+}
+
+int Map::insert_device(const float4* d_pts, int n) {
+    if (n <= 0) return FL_OK;
+    // worst case one fresh overflow leaf per point: guarantee the pool can take the batch
+    if ((long long)h_counters_[C_LEAF_USED] + n > v_.leaf_cap) {
+        min_pool_ = std::max(min_pool_, n + 1024);
+        FL_CHECK(rebuild());            // re-packs the leaves and re-sizes the pool
+    }
+    k_insert<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, n, counters_.as<int>());
+    FL_CUDA(cudaGetLastError());
+    FL_CUDA(cudaMemcpyAsync(h_counters_, counters_.ptr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaStreamSynchronize(stream_));
+    if (h_counters_[C_ERROR]) { set_last_error("insert: overflow pool exhausted"); return FL_ERR_CAPACITY; }
+    n_valid_ += n;
+    return FL_OK;
+}
+
+int Map::add_points_device(const float4* d_pts, int n, bool downsample_on, int* added) {
+    if (added) *added = 0;
+    if (n < 0) { set_last_error("add_points: n < 0"); return FL_ERR_ARG; }
+    if (n == 0) return FL_OK;
+    FL_CUDA(cudaSetDevice(device_));
+    if (!downsample_on) {                                   // ikd_Tree.cpp:549-568: plain inserts, return value 0
+        FL_CHECK(insert_device(d_pts, n));
+        return maybe_rebuild();
+    }
+    FL_CHECK(keys_in_.reserve(sizeof(unsigned long long) * (size_t)n));
+    FL_CHECK(keys_out_.reserve(sizeof(unsigned long long) * (size_t)n));
+    FL_CHECK(vals_in_.reserve(sizeof(unsigned) * (size_t)n));
+    FL_CHECK(vals_out_.reserve(sizeof(unsigned) * (size_t)n));
+    FL_CHECK(scratch2_.reserve(sizeof(int) * (size_t)n));          // group starts
+    FL_CHECK(scratch3_.reserve(sizeof(float4) * (size_t)n));       // insert list
+    int* d_cnt = counters_.as<int>();
+    FL_CUDA(cudaMemsetAsync(&d_cnt[C_ADDED], 0, sizeof(int) * 4, stream_));   // ADDED, GROUPS, NINSERT, TOMB
+    k_voxel_keys<<<blocks_for(n, 256, 1 << 30), 256, 0, stream_>>>(d_pts, n, downsample_, keys_in_.as<unsigned long long>(), vals_in_.as<unsigned>());
+    size_t tmp = 0;
+    FL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in_.as<unsigned long long>(), keys_out_.as<unsigned long long>(),
+                                            vals_in_.as<unsigned>(), vals_out_.as<unsigned>(), n, 0, 63, stream_));
+    FL_CHECK(cub_tmp_.reserve(tmp));
+    tmp = cub_tmp_.bytes;
+    FL_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.ptr, tmp, keys_in_.as<unsigned long long>(), keys_out_.as<unsigned long long>(),
+                                            vals_in_.as<unsigned>(), vals_out_.as<unsigned>(), n, 0, 63, stream_));
+    k_group_heads<<<blocks_for(n, 256, 1 << 30), 256, 0, stream_>>>(keys_out_.as<unsigned long long>(), n, scratch2_.as<int>(), d_cnt);
+    k_downsample_resolve<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(
+        v_, d_pts, keys_out_.as<unsigned long long>(), vals_out_.as<unsigned>(), n, scratch2_.as<int>(), downsample_,
+        scratch3_.as<float4>(), d_cnt);
+    FL_CUDA(cudaGetLastError());
+    FL_CUDA(cudaMemcpyAsync(h_counters_, counters_.ptr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaStreamSynchronize(stream_));
+    const int n_ins = h_counters_[C_NINSERT], n_tomb = h_counters_[C_TOMB];
+    if (added) *added = h_counters_[C_ADDED];
+    n_valid_ -= n_tomb; n_tomb_ += n_tomb;
+    FL_CHECK(insert_device(scratch3_.as<float4>(), n_ins));
+    // tombstoned slots are reused by later inserts; they stop counting once re-occupied
+    n_tomb_ = std::max(0, n_tomb_ - n_ins);
+    return maybe_rebuild();
+}
+
+int Map::add_points(const float* pts_xyzi, int n, bool downsample_on, int* added) {
+    if (added) *added = 0;
+    if (n < 0 || (n > 0 && !pts_xyzi)) { set_last_error("add_points: bad arguments"); return FL_ERR_ARG; }
+    if (n == 0) return FL_OK;
+    FL_CUDA(cudaSetDevice(device_));
+    FL_CHECK(scratch_.reserve(sizeof(float4) * (size_t)n));
+    FL_CUDA(cudaMemcpyAsync(scratch_.ptr, pts_xyzi, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, stream_));
+    return add_points_device(scratch_.as<float4>(), n, downsample_on, added);
+}
+
+int Map::tree_range(float* box6) {
+    FL_CUDA(cudaSetDevice(device_));
+    // union of the top-level entity boxes
+    const int k = v_.n_levels - 1;
+    const int c = v_.count[k];
+    std::vector<float4> h(2 * (size_t)c);
+    FL_CUDA(cudaMemcpyAsync(h.data(), v_.ebox[k], sizeof(float4) * 2 * (size_t)c, cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaStreamSynchronize(stream_));
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < c; i++) {
+        lo[0] = std::min(lo[0], h[2 * i].x); lo[1] = std::min(lo[1], h[2 * i].y); lo[2] = std::min(lo[2], h[2 * i].z);
+        hi[0] = std::max(hi[0], h[2 * i + 1].x); hi[1] = std::max(hi[1], h[2 * i + 1].y); hi[2] = std::max(hi[2], h[2 * i + 1].z);
+    }
+    if (n_valid_ == 0) for (int a = 0; a < 3; a++) lo[a] = hi[a] = 0.f;        // memset(&range, 0, ...) ikd_Tree.cpp:114
+    for (int a = 0; a < 3; a++) { box6[a] = lo[a]; box6[3 + a] = hi[a]; }
+    return FL_OK;
+}
+
+}  // namespace fl

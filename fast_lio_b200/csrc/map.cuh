@@ -1,0 +1,176 @@
+// Device-side view of the point map and the warp-cooperative traversals over it.
+//
+// The reference's ikd-Tree (include/ikd-Tree/ikd_Tree.{h,cpp}) is a pointer-chasing
+// binary k-d tree with 176-byte nodes (ikd_Tree.h:59-82) and ~33 dependent node visits
+// per query.  Here the map is a flattened, implicit 32-ary bounding-volume hierarchy:
+//
+//   level 0   leaf buckets: 32 slots of float4 (x, y, z, flag) = 512 B, one coalesced
+//             warp load; points sorted by Morton key at build time, `fill` slots
+//             populated, the rest left free for incremental inserts;
+//   level k   entity e of level k (a leaf for k = 0, an internal node otherwise) has its
+//             AABB in ebox[k][e] (two float4: lo, hi) and its smallest Morton key in
+//             esep[k][e]; node j of level k+1 owns entities 32j .. 32j+31 of level k, so
+//             there are no child pointers at all and a warp tests all 32 children of a
+//             node with one box per lane.
+//
+// A query is served by one warp: every lane holds the query, the running k-best list is
+// replicated in registers, candidates are ranked with a hardware warp reduction
+// (redux.sync) and the traversal state of each level lives in registers (the recursion
+// over the <= 7 levels is unrolled at compile time), so there is no stack in memory.
+#pragma once
+#include "common.cuh"
+
+namespace fl {
+
+struct MapView {
+    float4* pts;                     // [leaf_cap * 32]  (x, y, z, as_float(flag)); flag 1 = valid
+    float* payload;                  // [leaf_cap * 32]  intensity of the point in that slot
+    int* next;                       // [leaf_cap]       overflow chain of a leaf, -1 = none
+    float4* ebox[MAX_LEVELS];        // [padded count * 2] AABB (lo, hi) of each entity of level k
+    unsigned long long* esep[MAX_LEVELS];  // [padded count] smallest Morton key of the entity
+    int count[MAX_LEVELS + 1];       // entities per level; count[n_levels] == 1 (the root)
+    int n_levels;                    // number of internal levels (>= 1)
+    int n_main;                      // leaves addressed by the implicit tree (== count[0])
+    int leaf_cap;                    // allocated leaves (main + overflow pool)
+    int* n_leaf_used;                // device counter: main + allocated overflow leaves
+};
+
+__device__ __forceinline__ bool slot_valid(const float4& p) { return __float_as_int(p.w) == 1; }
+
+// ----------------------------------------------------------------------------- k-best list
+// Replicated in every lane; ascending by distance.  Mirrors MANUAL_HEAP + PointType_CMP
+// (ikd_Tree.h:93-201) in effect: a candidate enters only if strictly closer than the
+// current k-th best (ikd_Tree.cpp:1088).
+struct KBest {
+    float d[KNN_K];
+    int idx[KNN_K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < KNN_K; i++) { d[i] = INFINITY; idx[i] = -1; }
+    }
+    __device__ __forceinline__ float worst() const { return d[KNN_K - 1]; }
+    __device__ __forceinline__ void insert(float nd, int nidx) {
+        // branch-free sorted insert (nd < d[K-1] guaranteed by the caller)
+#pragma unroll
+        for (int i = KNN_K - 1; i > 0; i--) {
+            bool shift = nd < d[i - 1];
+            bool here = !shift && nd < d[i];
+            float dn = shift ? d[i - 1] : (here ? nd : d[i]);
+            int in = shift ? idx[i - 1] : (here ? nidx : idx[i]);
+            d[i] = dn; idx[i] = in;
+        }
+        if (nd < d[0]) { d[0] = nd; idx[0] = nidx; }
+    }
+};
+
+// Visit one leaf bucket (and its overflow chain): each lane scores one slot, then the
+// (at most K) improving candidates are extracted in ascending order.
+__device__ __forceinline__ void knn_leaf(const MapView& m, int leaf, float qx, float qy, float qz,
+                                         KBest& kb, int lane) {
+    while (leaf >= 0) {
+        const int slot = leaf * LEAF + lane;
+        const float4 p = __ldg(&m.pts[slot]);
+        const int nxt = __ldg(&m.next[leaf]);
+        float d = slot_valid(p) ? sq_dist3(qx, qy, qz, p.x, p.y, p.z) : INFINITY;
+        // ascending extraction: after K extractions nothing left can beat the k-th best
+#pragma unroll 1
+        for (int it = 0; it < KNN_K; it++) {
+            unsigned key = (d < kb.worst()) ? __float_as_uint(d) : 0xffffffffu;   // d >= 0: bits order like floats
+            unsigned best = __reduce_min_sync(FULL, key);
+            if (best == 0xffffffffu) break;
+            unsigned who = __ballot_sync(FULL, key == best);
+            int src = __ffs(who) - 1;
+            kb.insert(__uint_as_float(best), leaf * LEAF + src);
+            if (lane == src) d = INFINITY;
+        }
+        leaf = nxt;
+    }
+}
+
+// Visit node `node` of level L (its children are entities of level L-1).  Children are
+// taken nearest-first and re-tested against the shrinking k-th best distance after each
+// return -- the same pruning rule as KD_TREE::Search (ikd_Tree.cpp:1097-1243).
+template <int L>
+__device__ __forceinline__ void knn_node(const MapView& m, int node, float qx, float qy, float qz,
+                                         KBest& kb, int lane) {
+    const int e = node * FAN + lane;
+    float di = INFINITY;
+    if (e < m.count[L - 1]) {
+        const float4 lo = __ldg(&m.ebox[L - 1][2 * e]);
+        const float4 hi = __ldg(&m.ebox[L - 1][2 * e + 1]);
+        di = box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+    }
+#pragma unroll 1
+    while (true) {
+        // order by distance (low 5 mantissa bits traded for the lane id; pruning stays exact)
+        unsigned key = (di < kb.worst()) ? ((__float_as_uint(di) & ~31u) | (unsigned)lane) : 0xffffffffu;
+        unsigned best = __reduce_min_sync(FULL, key);
+        if (best == 0xffffffffu) break;
+        const int c = best & 31;
+        if (lane == c) di = INFINITY;
+        if constexpr (L == 1) knn_leaf(m, node * FAN + c, qx, qy, qz, kb, lane);
+        else knn_node<L - 1>(m, node * FAN + c, qx, qy, qz, kb, lane);
+    }
+}
+
+// Exact k-nearest-neighbour search for one query by one warp.
+__device__ __forceinline__ void knn_query(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
+    kb.init();
+    switch (m.n_levels) {
+        case 1: knn_node<1>(m, 0, qx, qy, qz, kb, lane); break;
+        case 2: knn_node<2>(m, 0, qx, qy, qz, kb, lane); break;
+        case 3: knn_node<3>(m, 0, qx, qy, qz, kb, lane); break;
+        case 4: knn_node<4>(m, 0, qx, qy, qz, kb, lane); break;
+        case 5: knn_node<5>(m, 0, qx, qy, qz, kb, lane); break;
+        case 6: knn_node<6>(m, 0, qx, qy, qz, kb, lane); break;
+        default: knn_node<7>(m, 0, qx, qy, qz, kb, lane); break;
+    }
+}
+
+// ----------------------------------------------------------------------------- box query
+// Half-open membership test of Search_by_range / Delete_by_range (ikd_Tree.cpp:796,1263):
+//   vertex_min <= p < vertex_max  on every axis.
+__device__ __forceinline__ bool in_box(const float4& p, const float* bmin, const float* bmax) {
+    return bmin[0] <= p.x && bmax[0] > p.x && bmin[1] <= p.y && bmax[1] > p.y && bmin[2] <= p.z && bmax[2] > p.z;
+}
+// AABB-vs-box rejection, the negation of ikd_Tree.cpp:1253-1258
+__device__ __forceinline__ bool box_overlaps(const float4& lo, const float4& hi, const float* bmin, const float* bmax) {
+    if (bmax[0] <= lo.x || bmin[0] > hi.x) return false;
+    if (bmax[1] <= lo.y || bmin[1] > hi.y) return false;
+    if (bmax[2] <= lo.z || bmin[2] > hi.z) return false;
+    return true;
+}
+
+// Functor interface: f.leaf(leaf_index) is called warp-uniformly for every leaf (main
+// leaves only; the functor walks the overflow chain itself) whose AABB overlaps the box.
+template <int L, class F>
+__device__ __forceinline__ void box_node(const MapView& m, int node, const float* bmin, const float* bmax, F& f, int lane) {
+    const int e = node * FAN + lane;
+    bool hit = false;
+    if (e < m.count[L - 1]) {
+        const float4 lo = __ldg(&m.ebox[L - 1][2 * e]);
+        const float4 hi = __ldg(&m.ebox[L - 1][2 * e + 1]);
+        hit = box_overlaps(lo, hi, bmin, bmax);
+    }
+    unsigned mask = __ballot_sync(FULL, hit);
+    while (mask) {
+        const int c = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if constexpr (L == 1) f.leaf(node * FAN + c);
+        else box_node<L - 1, F>(m, node * FAN + c, bmin, bmax, f, lane);
+    }
+}
+template <class F>
+__device__ __forceinline__ void box_query(const MapView& m, const float* bmin, const float* bmax, F& f, int lane) {
+    switch (m.n_levels) {
+        case 1: box_node<1, F>(m, 0, bmin, bmax, f, lane); break;
+        case 2: box_node<2, F>(m, 0, bmin, bmax, f, lane); break;
+        case 3: box_node<3, F>(m, 0, bmin, bmax, f, lane); break;
+        case 4: box_node<4, F>(m, 0, bmin, bmax, f, lane); break;
+        case 5: box_node<5, F>(m, 0, bmin, bmax, f, lane); break;
+        case 6: box_node<6, F>(m, 0, bmin, bmax, f, lane); break;
+        default: box_node<7, F>(m, 0, bmin, bmax, f, lane); break;
+    }
+}
+
+}  // namespace fl

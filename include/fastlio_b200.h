@@ -1,0 +1,125 @@
+/* fastlio_b200.h -- C ABI of the B200-native FAST-LIO2 measurement-update path.
+ *
+ * The reference (hku-mars/FAST_LIO) has no FFI layer: the hot path is reached through two
+ * C++ class APIs used by src/laserMapping.cpp.  This header is the extern "C" boundary that
+ * sits underneath drop-in facades of those two classes (include/ikd-Tree/ikd_Tree.h and
+ * include/IKFoM_toolkit/esekfom/esekfom.hpp in this repository); each entry point cites
+ * the reference interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions: opaque handles; caller-owned HOST buffers unless a name says _device;
+ * every function returns an int status (0 = ok, <0 = error, see FL_ERR_*) except the
+ * counting queries; no exceptions cross the boundary; fl_last_error() returns a
+ * thread-local message.  One CUDA stream per map handle; handles are thread-compatible
+ * (serialise calls on one handle), distinct handles are independent.
+ *
+ * Point layout everywhere: 4 floats (x, y, z, intensity) -- the fields of
+ * pcl::PointXYZINormal (include/common_lib.h:37) that the path reads.
+ * State layout (26 doubles): pos(3) rot(x,y,z,w) offset_R_L_I(x,y,z,w) offset_T_L_I(3)
+ * vel(3) bg(3) ba(3) grav(3)  == state_ikfom (include/use-ikfom.hpp:12-21), quaternions in
+ * Eigen coeffs() order.  Covariance: 23 x 23 doubles, row-major, DOF order of state_ikfom.
+ */
+#ifndef FASTLIO_B200_H
+#define FASTLIO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FL_OK 0
+#define FL_ERR_CUDA (-1)
+#define FL_ERR_ARG (-2)
+#define FL_ERR_NCCL (-3)
+#define FL_ERR_STATE (-4)
+#define FL_ERR_CAPACITY (-5)
+
+typedef struct fl_map fl_map_t;        /* replaces KD_TREE<PointType>          include/ikd-Tree/ikd_Tree.h:48-341 */
+typedef struct fl_filter fl_filter_t;  /* replaces esekfom::esekf<state_ikfom,12,input_ikfom> + h_share_model */
+
+/* Same layout as the oracle's per-pass log; used by the parity tests. */
+typedef struct fl_pass_log {
+    int searched, valid, effct, converged;
+    double res_sum;
+    double HtH[144];
+    double Hth[12];
+    double x_after[26];
+} fl_pass_log_t;
+
+const char* fl_last_error(void);
+int fl_device_count(void);
+int fl_version(void);
+
+/* ------------------------------------------------------------------ map: KD_TREE<PointType> */
+/* KD_TREE::KD_TREE(delete_param, balance_param, box_length)          ikd_Tree.h:309, ikd_Tree.cpp:9-18
+ * (the two rebuild criteria have no counterpart: leaves are re-packed by fl_map_rebuild / automatically) */
+int fl_map_create(fl_map_t** out, int device, float downsample_size);
+int fl_map_destroy(fl_map_t* m);
+/* KD_TREE::set_downsample_param                                      ikd_Tree.h:319-322 */
+int fl_map_set_downsample(fl_map_t* m, float downsample_size);
+/* KD_TREE::Build(PointVector)                                        ikd_Tree.cpp:409-423 */
+int fl_map_build(fl_map_t* m, const float* pts_xyzi, int n);
+/* KD_TREE::size() / validnum()                                       ikd_Tree.cpp:70-97, 140-163 */
+int fl_map_size(fl_map_t* m);
+int fl_map_validnum(fl_map_t* m);
+/* KD_TREE::Nearest_Search, batched over nq queries, k <= 5           ikd_Tree.cpp:426-461
+ * out_pts: nq*k*4 floats (ascending distance), out_d2: nq*k floats, out_cnt: nq ints.  Safe for
+ * concurrent host callers on one handle (internally serialised). */
+int fl_map_knn(fl_map_t* m, const float* q_xyzi, int nq, int k, float* out_pts, float* out_d2, int* out_cnt);
+/* KD_TREE::Add_Points(PointVector&, bool downsample_on) -> int       ikd_Tree.cpp:478-573
+ * returns the reference's return value (>= 0) or an error (< 0) */
+int fl_map_add_points(fl_map_t* m, const float* pts_xyzi, int n, int downsample_on);
+/* KD_TREE::Delete_Point_Boxes(vector<BoxPointType>&) -> int          ikd_Tree.cpp:632-658
+ * boxes6: nb * (min xyz, max xyz); returns the number of points invalidated or an error (< 0) */
+int fl_map_delete_boxes(fl_map_t* m, const float* boxes6, int nb);
+/* KD_TREE::flatten(Root_Node, Storage, NOT_RECORD): all valid points  ikd_Tree.cpp:1627-1658
+ * returns the number of valid points (writes at most cap of them) or an error (< 0) */
+int fl_map_flatten(fl_map_t* m, float* out_xyzi, int cap);
+/* KD_TREE::tree_range()                                              ikd_Tree.cpp:100-137 */
+int fl_map_tree_range(fl_map_t* m, float* box6);
+/* KD_TREE::Rebuild of the whole tree (ikd_Tree.cpp:736-764): re-sorts all valid points into fresh leaves */
+int fl_map_rebuild(fl_map_t* m);
+/* introspection: [0] main leaves [1] overflow leaves [2] internal levels [3] rebuilds so far */
+int fl_map_stats(fl_map_t* m, int* out4);
+
+/* ------------------------------------------------------------------ filter: esekf + h_share_model */
+/* esekf::esekf + esekf::init_dyn_share(f, f_x, f_w, h_share_model, maximum_iteration, limit)
+ *                                                                   esekfom.hpp:238-254, laserMapping.cpp:826-828 */
+int fl_filter_create(fl_filter_t** out, fl_map_t* map, int max_points);
+int fl_filter_destroy(fl_filter_t* f);
+/* maximum_iter, limit[23], extrinsic_est_en (laserMapping.cpp:739,789) */
+int fl_filter_set_params(fl_filter_t* f, int max_iter, const double* limit23, int extrinsic_est_en);
+/* 0: information form with two 23x23 inversions as written at esekfom.hpp:1782-1809 (default);
+ * 1: the same gain through one 12x12 solve */
+int fl_filter_set_solver(fl_filter_t* f, int mode);
+/* esekf::update_iterated_dyn_share_modified(R, solve_time) with feats_down_body bound
+ *                                                                   esekfom.hpp:1619-1931, laserMapping.cpp:638-754, :960
+ * x26 / P: in = kf.get_x()/get_P() before the update, out = after.  solve_time_s (may be NULL)
+ * is incremented by the device time of the update, like the reference's out-parameter. */
+int fl_filter_update(fl_filter_t* f, const float* body_xyzi, int nq, double* x26, double* P, double R, double* solve_time_s);
+/* Nearest_Points after the update (laserMapping.cpp:102, read by map_incremental :438-460) */
+int fl_filter_get_nearest(fl_filter_t* f, float* out_pts, int* out_cnt, int nq);
+/* point_selected_surf after the update (laserMapping.cpp:76) */
+int fl_filter_get_selected(fl_filter_t* f, unsigned char* out, int nq);
+/* per-pass H^T H, H^T h, effct_feat_num, total_residual, state -- for parity tests / the reference's debug log */
+int fl_filter_get_pass_logs(fl_filter_t* f, fl_pass_log_t* out, int cap);
+/* pieces of fl_filter_update for pipelines that keep the scan resident in HBM */
+int fl_filter_upload_scan(fl_filter_t* f, const float* body_xyzi, int nq);
+int fl_filter_upload_state(fl_filter_t* f, const double* x26, const double* P, double R);
+int fl_filter_run(fl_filter_t* f);                 /* enqueue all passes, asynchronous */
+int fl_filter_download_state(fl_filter_t* f, double* x26, double* P, int* n_pass);   /* synchronises */
+int fl_filter_sync(fl_filter_t* f);
+/* device time in milliseconds of `reps` back-to-back resident updates from the uploaded state
+ * (CUDA events on the handle's stream); optionally flushes L2 between repetitions */
+int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_total);
+int fl_filter_gpu_launches(fl_filter_t* f);
+
+/* ------------------------------------------------------------------ multi-GPU (no reference counterpart)
+ * scan points are sharded across ranks, the map is replicated, the 92 normal-equation doubles
+ * are all-reduced once per pass (NCCL over NVLink) and every rank solves redundantly. */
+int fl_comm_unique_id(void* out128);
+int fl_filter_comm_init(fl_filter_t* f, int nranks, int rank, const void* unique_id128);
+int fl_filter_set_shard(fl_filter_t* f, int q_begin, int q_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTLIO_B200_H */

@@ -43,7 +43,7 @@ SYMBOLS = [
     "fl_filter_create", "fl_filter_destroy", "fl_filter_set_params", "fl_filter_set_solver", "fl_filter_update",
     "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
     "fl_filter_upload_state", "fl_filter_run", "fl_filter_download_state", "fl_filter_sync",
-    "fl_filter_time_resident", "fl_filter_gpu_launches",
+    "fl_filter_time_resident", "fl_filter_time_search_pass", "fl_filter_gpu_launches",
     "fl_comm_unique_id", "fl_filter_comm_init", "fl_filter_set_shard",
 ]
 
@@ -89,6 +89,7 @@ def load():
     L.fl_filter_download_state.argtypes = [C.c_void_p, _f64p, _f64p, C.POINTER(C.c_int)]
     L.fl_filter_sync.argtypes = [C.c_void_p]
     L.fl_filter_time_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.fl_filter_time_search_pass.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.fl_filter_gpu_launches.argtypes = [C.c_void_p]
     L.fl_comm_unique_id.argtypes = [C.c_char_p]
     L.fl_filter_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
@@ -262,6 +263,11 @@ class Esekf:
     def time_resident(self, reps: int, flush_l2: bool = True) -> float:
         ms = C.c_float(0.0)
         _check(self._L.fl_filter_time_resident(self.h, reps, int(flush_l2), C.byref(ms)))
+        return ms.value
+
+    def time_search_pass(self, reps: int, flush_l2: bool = True) -> float:
+        ms = C.c_float(0.0)
+        _check(self._L.fl_filter_time_search_pass(self.h, reps, int(flush_l2), C.byref(ms)))
         return ms.value
 
     def gpu_launches(self) -> int:

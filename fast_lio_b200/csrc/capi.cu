@@ -19,7 +19,6 @@ struct fl_filter {
     fl::Filter* impl;
     fl_map* map;
     fl::DeviceBuffer flush;
-    fl::DeviceBuffer ctl0;
 };
 
 static_assert(sizeof(fl_pass_log_t) == sizeof(fl::PassLog), "pass-log layouts must match");
@@ -117,7 +116,7 @@ int fl_filter_create(fl_filter_t** out, fl_map_t* map, int max_points) {
 }
 int fl_filter_destroy(fl_filter_t* f) {
     if (!f) return FL_OK;
-    f->flush.release(); f->ctl0.release();
+    f->flush.release();
     delete f->impl;
     delete f;
     return FL_OK;
@@ -146,6 +145,12 @@ int fl_filter_upload_state(fl_filter_t* f, const double* x26, const double* P, d
 int fl_filter_run(fl_filter_t* f) { FILTER_GUARD(f); return f->impl->run_passes(); }
 int fl_filter_download_state(fl_filter_t* f, double* x26, double* P, int* n_pass) { FILTER_GUARD(f); return f->impl->download_state(x26, P, n_pass); }
 int fl_filter_sync(fl_filter_t* f) { FILTER_GUARD(f); return f->impl->sync(); }
+int fl_filter_debug_prof(fl_filter_t* f, long long* out16) {
+    FILTER_GUARD(f);
+    if (!out16) return FL_ERR_ARG;
+    FL_CUDA(cudaMemcpy(out16, f->impl->ctl_device()->prof, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+    return FL_OK;
+}
 int fl_filter_gpu_launches(fl_filter_t* f) { FILTER_GUARD(f); return f->impl->gpu_launches(); }
 
 int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_total) {
@@ -154,9 +159,6 @@ int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_to
     fl::Filter* F = f->impl;
     cudaStream_t st = F->stream();
     FL_CUDA(cudaSetDevice(F->map()->device()));
-    const size_t ctl_bytes = offsetof(fl::FilterCtl, P_prop);
-    FL_CHECK(f->ctl0.reserve(ctl_bytes));
-    FL_CUDA(cudaMemcpyAsync(f->ctl0.ptr, F->ctl_device(), ctl_bytes, cudaMemcpyDeviceToDevice, st));
     const size_t flush_bytes = 256u << 20;       // > 126 MB of L2
     if (flush_l2) FL_CHECK(f->flush.reserve(flush_bytes));
     cudaEvent_t e0, e1;
@@ -164,7 +166,7 @@ int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_to
     FL_CUDA(cudaEventCreate(&e1));
     float total = 0.f;
     for (int r = 0; r < reps; r++) {
-        FL_CUDA(cudaMemcpyAsync((void*)F->ctl_device(), f->ctl0.ptr, ctl_bytes, cudaMemcpyDeviceToDevice, st));
+        FL_CHECK(F->restore_state());
         if (flush_l2) FL_CUDA(cudaMemsetAsync(f->flush.ptr, r & 0xff, flush_bytes, st));
         FL_CUDA(cudaEventRecord(e0, st));
         int rc = F->run_passes();
@@ -177,6 +179,39 @@ int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_to
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    *ms_total = total;
+    return FL_OK;
+}
+
+// Device time of the dominant kernel alone: k_search (the kNN of the first pass of an update).
+int fl_filter_time_search_pass(fl_filter_t* f, int reps, int flush_l2, float* ms_total) {
+    FILTER_GUARD(f);
+    if (reps < 1 || !ms_total) return FL_ERR_ARG;
+    fl::Filter* F = f->impl;
+    cudaStream_t st = F->stream();
+    FL_CUDA(cudaSetDevice(F->map()->device()));
+    const size_t flush_bytes = 256u << 20;
+    if (flush_l2) FL_CHECK(f->flush.reserve(flush_bytes));
+    cudaEvent_t e0, e1;
+    FL_CUDA(cudaEventCreate(&e0));
+    FL_CUDA(cudaEventCreate(&e1));
+    float total = 0.f;
+    for (int r = 0; r < reps; r++) {
+        FL_CHECK(F->restore_state());
+        if (flush_l2) FL_CUDA(cudaMemsetAsync(f->flush.ptr, r & 0xff, flush_bytes, st));
+        FL_CUDA(cudaEventRecord(e0, st));
+        int rc = F->launch_search_only();
+        if (rc != FL_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+        FL_CUDA(cudaEventRecord(e1, st));
+        FL_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        FL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // leave the control block as uploaded
+    FL_CHECK(F->restore_state());
     *ms_total = total;
     return FL_OK;
 }

@@ -15,12 +15,13 @@
 #include <algorithm>
 
 #include "filter.h"
+#include "gj.cuh"
 
 namespace fl {
 
 constexpr int PSTRIDE = 96;          // doubles per partial row (NRED = 92 padded)
-constexpr int MEASURE_THREADS = 256;
-constexpr int SOLVE_THREADS = 512;
+constexpr int SEARCH_THREADS = 256;
+constexpr int RESID_THREADS = 256;
 constexpr int MAX_LOGS = 16;
 
 __device__ __forceinline__ int tri12(int a, int b) { return a * 12 - (a * (a - 1)) / 2 + (b - a); }   // a <= b
@@ -258,125 +259,48 @@ __device__ __forceinline__ void warp_accumulate(bool contrib, const double* h, d
     }
 }
 
-// One launch per iEKF pass.  Search passes: one warp per scan point (kNN), then the per-point
-// tail thread-parallel over the points the warp has served.  Non-search passes: one thread per
-// point.  Which of the two runs is decided on the device (ctl->converge), so the launch sequence
-// of a scan is fixed and needs no host synchronisation.
-template <bool EXTR>
-__global__ void __launch_bounds__(MEASURE_THREADS) k_measure(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl,
-                                                              double* __restrict__ partials) {
-    if (ctl->done) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int warps_per_block = MEASURE_THREADS / 32;
-    const int gwarp = blockIdx.x * warps_per_block + warp;
-    const int nwarps = gridDim.x * warps_per_block;
-    const bool search = ctl->converge != 0;
-    const PoseS s = load_pose(ctl->x);
-    double acc[3] = {0.0, 0.0, 0.0};
+// k_search -- the kNN half of h_share_model (laserMapping.cpp:667-672).  One warp per scan
+// point, a contiguous run of points per warp: the lanes first transform the warp's points to the
+// world frame thread-parallel (FP64, laserMapping.cpp:656-661), then the warp walks the map once
+// per point.  Runs only when the filter asks for a search (ekfom_data.converge, decided on the
+// device); few registers, so that many warps hide the latency of the dependent tree loads.
+__global__ void __launch_bounds__(SEARCH_THREADS) k_search(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
+    if (ctl->done || !ctl->converge) return;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * SEARCH_THREADS + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * SEARCH_THREADS) >> 5;
     const int q0 = sc.q_begin, q1 = sc.q_end;
-
-    if (search) {
-        int mine = -1;          // the query this lane will run the tail for
-        int n_mine = 0;
-        for (int q = q0 + gwarp; q < q1; q += nwarps) {
-            const float4 pb = __ldg(&sc.body[q]);
-            float wx, wy, wz;
-            body_to_world(s, pb, wx, wy, wz);
+    const int per_warp = (q1 - q0 + nwarps - 1) / nwarps;
+    const int wq0 = q0 + gwarp * per_warp;
+    const int wq1 = min(q1, wq0 + per_warp);
+    for (int base = wq0; base < wq1; base += 32) {
+        const int myq = base + lane;
+        float wx = 0.f, wy = 0.f, wz = 0.f;
+        if (myq < wq1) {
+            const PoseS s = load_pose(ctl->x);
+            body_to_world(s, __ldg(&sc.body[myq]), wx, wy, wz);
+        }
+        const int cnt_chunk = min(32, wq1 - base);
+        for (int l = 0; l < cnt_chunk; l++) {
+            const float qx = __shfl_sync(FULL, wx, l), qy = __shfl_sync(FULL, wy, l), qz = __shfl_sync(FULL, wz, l);
+            const int q = base + l;
             KBest kb;
-            knn_query(m, wx, wy, wz, kb, lane);
-            int myidx = -1;
-#pragma unroll
-            for (int j = 0; j < KNN_K; j++) if (lane == j) myidx = kb.idx[j];
+            knn_query(m, qx, qy, qz, kb, lane);
+            const int cnt = __popc(__ballot_sync(FULL, lane < KNN_K && kb.idx >= 0));
             if (lane < KNN_K) {
                 float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (myidx >= 0) { p = m.pts[myidx]; p.w = m.payload[myidx]; }
+                if (kb.idx >= 0) { p = m.pts[kb.idx]; p.w = m.payload[kb.idx]; }
                 sc.nearest[(size_t)q * KNN_K + lane] = p;
             }
-            if (lane == 0) {
-                int cnt = 0;
-#pragma unroll
-                for (int j = 0; j < KNN_K; j++) cnt += kb.idx[j] >= 0 ? 1 : 0;
+            if (lane == KNN_K - 1) {
                 sc.nearest_cnt[q] = cnt;
-                // laserMapping.cpp:671
-                sc.selected[q] = (cnt < KNN_K) ? 0 : (kb.d[KNN_K - 1] > 5.0f ? 0 : 1);
-            }
-            if (lane == n_mine) mine = q;
-            n_mine++;
-            if (n_mine == 32) {
-                __syncwarp();
-                double h[12]; double z = 0.0; float ar = 0.f;
-                const bool contrib = measure_point<EXTR>(sc, mine, s, h, z, ar);
-                warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane);
-                n_mine = 0; mine = -1;
+                sc.selected[q] = (cnt < KNN_K) ? 0 : (kb.d > 5.0f ? 0 : 1);          // laserMapping.cpp:671
             }
         }
-        if (__any_sync(FULL, n_mine > 0)) {
-            __syncwarp();
-            double h[12]; double z = 0.0; float ar = 0.f;
-            bool contrib = false;
-            if (lane < n_mine) contrib = measure_point<EXTR>(sc, mine, s, h, z, ar);
-            warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane);
-        }
-    } else {
-        for (int base = q0 + gwarp * 32; base < q1; base += nwarps * 32) {
-            const int q = base + lane;
-            double h[12]; double z = 0.0; float ar = 0.f;
-            bool contrib = false;
-            if (q < q1) contrib = measure_point<EXTR>(sc, q, s, h, z, ar);
-            warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane);
-        }
-    }
-    // deterministic block partial: warps -> shared -> fixed-order sum
-    __shared__ double wacc[MEASURE_THREADS / 32][PSTRIDE];
-#pragma unroll
-    for (int j = 0; j < 3; j++) wacc[warp][lane + 32 * j] = acc[j];
-    __syncthreads();
-    if (threadIdx.x < PSTRIDE) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < MEASURE_THREADS / 32; w++) v += wacc[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * PSTRIDE + threadIdx.x] = v;
     }
 }
 
 // ============================================================================= solve
-// Gauss-Jordan with (logical) partial pivoting on an n x nc augmented system [A | B] held in
-// shared memory; on return  A^{-1} B  is read through row_of[]:  X[k][j] = a[row_of[k]][n + j] / a[row_of[k]][k].
-__device__ bool gj_eliminate(double* a, int n, int nc, int ld, double* colbuf, int* row_of, int* used, int* s_piv) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid < n) used[tid] = 0;
-    __syncthreads();
-    bool ok = true;
-    for (int k = 0; k < n; k++) {
-        if (tid < 32) {
-            double best = -1.0; int bi = -1;
-            if (tid < n && !used[tid]) { best = fabs(a[tid * ld + k]); bi = tid; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(FULL, best, o);
-                const int oi = __shfl_xor_sync(FULL, bi, o);
-                if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
-            }
-            if (tid == 0) { *s_piv = (best > 0.0) ? bi : -1; }
-        }
-        __syncthreads();
-        const int p = *s_piv;
-        if (p < 0) { ok = false; break; }
-        const double pv = a[p * ld + k];
-        if (tid < n) colbuf[tid] = (tid == p) ? 0.0 : a[tid * ld + k] / pv;
-        if (tid == 0) { used[p] = 1; row_of[k] = p; }
-        __syncthreads();
-        for (int e = tid; e < n * nc; e += nt) {
-            const int i = e / nc, j = e % nc;
-            const double f = colbuf[i];
-            if (f != 0.0) a[i * ld + j] -= f * a[p * ld + j];
-        }
-        __syncthreads();
-    }
-    return ok;
-}
-
-
 struct SolveShared {
     double red[PSTRIDE];
     double HTH[144];
@@ -387,14 +311,14 @@ struct SolveShared {
     double Kx[NDOF * 12];         // K_x[:, 0:12]   (columns 12..22 are zero in every branch)
     double Kh[NDOF];
     double dx[NDOF], dx_new[NDOF], dxu[NDOF];
-    double J[2][9];
-    double M2[4];
+    double J[2][9];               // A_matrix(.)^T of the two SO3 blocks (rot, offset_R_L_I)
+    double M2[4];                 // Nx * Mx of the S2 block (grav)
     double xnew[XLEN];
-    double colbuf[32];
     double rows[22 * 13];         // small-m branch: [h_x row (12) | h]
     double PHt[NDOF * 22];        // small-m branch
-    double T[22 * 13];            // small-m branch: S^{-1} [h_x | h]
-    int row_of[32], used[32], piv, m_rows, finish;
+    double T[22 * 13];            // S^{-1} [h_x | h]  /  (I + M A11)^{-1} [H^T h | H^T H]
+    double wred[8 * PSTRIDE];     // per-warp partial sums of the cross-block reduction
+    int row_of[32], m_rows, finish, over, prep_ok;
     int row_idx[22];
 };
 
@@ -417,9 +341,9 @@ __device__ void apply_rows(double* dst, const double* src, const double* J3, con
     }
 }
 // columns {3..5, 6..8, 21..22} of the 23x23 `mat` := (row block) * J^T, for every row
-__device__ void apply_cols(double* mat, const double* J3, const double* J6, const double* M2) {
-    const int i = threadIdx.x;
-    if (i < NDOF) {
+__device__ void apply_cols(double* mat, const double* J3, const double* J6, const double* M2, int first_thread) {
+    const int i = (int)threadIdx.x - first_thread;
+    if (i >= 0 && i < NDOF) {
 #pragma unroll
         for (int b = 0; b < 2; b++) {
             const int idx = b == 0 ? 3 : 6;
@@ -434,93 +358,121 @@ __device__ void apply_cols(double* mat, const double* J3, const double* J6, cons
         mat[i * NDOF + 22] = a * M2[2] + bq * M2[3];
     }
 }
-// thread 0: the three congruence blocks for the tangent vector d (esekfom.hpp:1659-1690 / 1836-1876)
-__device__ void make_congruence(const double* d, const double* x_now, const double* x_prop, double (*J)[9], double* M2) {
-    for (int b = 0; b < 2; b++) {
-        const int idx = b == 0 ? 3 : 6;
-        M33 Jm = transpose33(A_matrix(d3(d[idx], d[idx + 1], d[idx + 2])));        // T5: A_matrix(dx)^T
-        for (int i = 0; i < 9; i++) J[b][i] = Jm.m[i];
-    }
-    S2_congruence(ld3(x_now + X_GRAV), ld3(x_prop + X_GRAV), d[21], d[22], M2);
-}
 
-// mode 0: reduce the block partials and solve (single GPU);
-// mode 1: reduce only -> red_g (an all-reduce over the ranks follows);
-// mode 2: solve from red_g.
-__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(FilterCtl* ctl, const double* __restrict__ partials, int n_partials,
-                                                          double* red_g, int mode, ScanView sc, PassLog* logs, int solver) {
-    __shared__ SolveShared S;
-    const int tid = threadIdx.x, nt = blockDim.x;
+// ----------------------------------------------------------------------------- the Kalman step of one pass
+// Split in two so that the part that does not depend on this pass's residuals can run while the
+// other blocks are still computing them:
+//   solve_prepare : dx = x [-] x_prop, the manifold congruence blocks, P := T P_prop T^T
+//                   (esekfom.hpp:1651-1699) and, for the reference-form solver, (P/R)^{-1};
+//   solve_finish  : gain, dx_, boxplus, convergence bookkeeping, final covariance
+//                   (esekfom.hpp:1715-1927), from the reduced normal equations in S.red.
+// Both are block-wide (blockDim >= 160).  The scalar manifold work is spread over the first lanes
+// of different warps so that the FP64 chains (and their instruction fetches) overlap.
+#define STAMP(i) do { if (threadIdx.x == 0) ctl->prof[i] = clock64(); } while (0)
+
+__device__ __noinline__ void solve_prepare(SolveShared& S, const FilterCtl* ctl, int solver) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     constexpr int n = NDOF;
-    if (ctl->done) return;
-    // ------------------------------------------------------------------ reduce
-    if (mode != 2) {
-        const int o = tid >> 2, sub = tid & 3;
-        double v = 0.0;
-        if (o < NRED) for (int b = sub; b < n_partials; b += 4) v += partials[(size_t)b * PSTRIDE + o];
-        v += __shfl_xor_sync(FULL, v, 1);
-        v += __shfl_xor_sync(FULL, v, 2);
-        if (o < NRED && sub == 0) { S.red[o] = v; if (mode == 1) red_g[o] = v; }
-        if (mode == 1) return;
-    } else {
-        if (tid < NRED) S.red[tid] = red_g[tid];
-    }
-    __syncthreads();
-    if (tid < 144) { const int a = tid / 12, b = tid % 12; S.HTH[tid] = S.red[a <= b ? tri12(a, b) : tri12(b, a)]; }
-    if (tid < 12) S.Hth[tid] = S.red[78 + tid];
-    const int effct = (int)(S.red[90] + 0.5);
-    const int it = ctl->iter, max_iter = ctl->max_iter, n_pass = ctl->n_pass;
-    const int searched = ctl->converge;
-    const int t_in = ctl->t;
-    const double R = ctl->R;
-    PassLog* lg = (logs && n_pass < MAX_LOGS) ? &logs[n_pass] : nullptr;
-    __syncthreads();
-    if (lg) {
-        if (tid < 144) lg->HtH[tid] = S.HTH[tid];
-        if (tid < 12) lg->Hth[tid] = S.Hth[tid];
-        if (tid == 0) { lg->searched = searched; lg->effct = effct; lg->res_sum = S.red[91]; lg->valid = effct >= 1; }
-    }
-    // ------------------------------------------------------------------ invalid pass (laserMapping.cpp:708-713, esekfom.hpp:1638-1641)
-    if (effct < 1) {
-        if (tid == 0) {
-            if (lg) { lg->converged = searched; for (int i = 0; i < XLEN; i++) lg->x_after[i] = ctl->x[i]; }
-            ctl->n_pass = n_pass + 1;
-            ctl->iter = it + 1;
-            if (it + 1 >= max_iter) ctl->done = 1;
+    if (lane == 0) {
+        if (warp < 2) {                 // SO3 blocks: rot (idx 3), offset_R_L_I (idx 6)
+            const int idx = warp == 0 ? 3 : 6, xo = warp == 0 ? X_ROT : X_OFFR;
+            const D3 l = so3_log(qmul(qconj(ldq(ctl->x_prop + xo)), ldq(ctl->x + xo)));            // SOn.hpp:237-239
+            const M33 J = transpose33(A_matrix(l));                                                 // T5
+#pragma unroll 1
+            for (int i = 0; i < 9; i++) S.J[warp][i] = J.m[i];
+            const D3 seg = mul33v(J, l);
+            S.dx[idx] = l.x; S.dx[idx + 1] = l.y; S.dx[idx + 2] = l.z;
+            S.dx_new[idx] = seg.x; S.dx_new[idx + 1] = seg.y; S.dx_new[idx + 2] = seg.z;
+        } else if (warp == 2) {         // S2 block: grav (idx 21)
+            double d0, d1;
+            S2_boxminus(ld3(ctl->x + X_GRAV), ld3(ctl->x_prop + X_GRAV), d0, d1);
+            S2_congruence(ld3(ctl->x + X_GRAV), ld3(ctl->x_prop + X_GRAV), d0, d1, S.M2);
+            S.dx[21] = d0; S.dx[22] = d1;
+            S.dx_new[21] = S.M2[0] * d0 + S.M2[1] * d1;
+            S.dx_new[22] = S.M2[2] * d0 + S.M2[3] * d1;
         }
-        return;
     }
-    // ------------------------------------------------------------------ esekfom.hpp:1651-1699
-    if (tid == 0) {
-        state_boxminus(ctl->x, ctl->x_prop, S.dx);
-        for (int i = 0; i < n; i++) S.dx_new[i] = S.dx[i];
-        make_congruence(S.dx, ctl->x, ctl->x_prop, S.J, S.M2);
-        for (int b = 0; b < 2; b++) {
-            const int idx = b == 0 ? 3 : 6;
-            const double* J = S.J[b];
-            const double v0 = S.dx_new[idx], v1 = S.dx_new[idx + 1], v2 = S.dx_new[idx + 2];
-            S.dx_new[idx] = J[0] * v0 + J[1] * v1 + J[2] * v2;
-            S.dx_new[idx + 1] = J[3] * v0 + J[4] * v1 + J[5] * v2;
-            S.dx_new[idx + 2] = J[6] * v0 + J[7] * v1 + J[8] * v2;
-        }
-        const double d0 = S.M2[0] * S.dx_new[21] + S.M2[1] * S.dx_new[22];
-        const double d1 = S.M2[2] * S.dx_new[21] + S.M2[3] * S.dx_new[22];
-        S.dx_new[21] = d0; S.dx_new[22] = d1;
+    if (warp == 3 && lane < 15) {       // vect blocks: pos, offset_T_L_I, vel, bg, ba
+        const int b = lane / 3, c = lane % 3;
+        const int dof = b == 0 ? 0 : 9 + 3 * (b - 1);
+        const int xo = b == 0 ? X_POS : (b == 1 ? X_OFFT : (b == 2 ? X_VEL : (b == 3 ? X_BG : X_BA)));
+        const double d = ctl->x[xo + c] - ctl->x_prop[xo + c];
+        S.dx[dof + c] = d; S.dx_new[dof + c] = d;
     }
+#pragma unroll 1
     for (int e = tid; e < n * n; e += nt) S.P[e] = ctl->P_prop[e];
     __syncthreads();
     // The reference interleaves row/column products per block (rows3, cols3, rows6, cols6, rows21,
     // cols21); the blocks act on disjoint index sets, so P := T P T^T either way.
     apply_rows(S.P, S.P, S.J[0], S.J[1], S.M2, n, n);
     __syncthreads();
-    apply_cols(S.P, S.J[0], S.J[1], S.M2);
+    apply_cols(S.P, S.J[0], S.J[1], S.M2, 0);
     __syncthreads();
+    S.prep_ok = 1;
+    if (solver == 0) {
+        // first half of esekfom.hpp:1782:  P_temp = (P/R)^{-1}  -> S.L  (independent of H)
+        const double R = ctl->R;
+#pragma unroll 1
+        for (int e = tid; e < n * 2 * n; e += nt) {
+            const int i = e / (2 * n), j = e % (2 * n);
+            S.aug[e] = j < n ? S.P[i * n + j] / R : (j - n == i ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        const bool ok = gj_eliminate(S.aug, n, 2 * n, 2 * n, S.row_of);
+        if (ok) {
+#pragma unroll 1
+            for (int e = tid; e < n * n; e += nt) {
+                const int k = e / n, j = e % n;
+                const int pr = S.row_of[k];
+                S.L[e] = S.aug[pr * 2 * n + n + j] / S.aug[pr * 2 * n + k];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) S.prep_ok = ok ? 1 : 0;
+        __syncthreads();
+    }
+}
 
-    bool ok = true;
-    if (effct < n) {
+__device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const ScanView& sc, PassLog* logs, int solver) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int n = NDOF;
+    STAMP(1);
+    if (tid < 144) { const int a = tid / 12, b = tid % 12; S.HTH[tid] = S.red[a <= b ? tri12(a, b) : tri12(b, a)]; }
+    if (tid < 12) S.Hth[tid] = S.red[78 + tid];
+    const int effct = (int)(S.red[90] + 0.5);
+    const int it = ctl->iter, max_iter = ctl->max_iter, n_pass = ctl->n_pass;
+    const int searched = ctl->converge;
+    const int t_in = ctl->t;
+    const int extr = ctl->extrinsic_est;
+    const double R = ctl->R;
+    PassLog* lg = (logs && n_pass < MAX_LOGS) ? &logs[n_pass] : nullptr;
+    // ------------------------------------------------------------------ invalid pass (laserMapping.cpp:708-713, esekfom.hpp:1638-1641)
+    if (effct < 1) {
+        if (tid == 0) {
+            if (lg) {
+                lg->searched = searched; lg->effct = 0; lg->res_sum = 0.0; lg->valid = 0;
+                lg->converged = searched; for (int i = 0; i < XLEN; i++) lg->x_after[i] = ctl->x[i];
+            }
+            ctl->n_pass = n_pass + 1;
+            ctl->iter = it + 1;
+            if (it + 1 >= max_iter) ctl->done = 1;
+        }
+        return;
+    }
+    __syncthreads();
+    if (lg) {
+        if (tid < 144) lg->HtH[tid] = S.HTH[tid];
+        if (tid < 12) lg->Hth[tid] = S.Hth[tid];
+        if (tid == 0) { lg->searched = searched; lg->effct = effct; lg->res_sum = S.red[91]; lg->valid = 1; }
+    }
+    bool ok = S.prep_ok != 0;
+    const int ne = extr ? 12 : 6;          // with extrinsic_est_en == false, columns 6..11 of h_x are zero
+    if (!ok) {
+        // fall through to the error exit below
+    } else if (effct < n) {
         // -------------------------------------------------------------- small-m branch, esekfom.hpp:1715-1744 (T6)
         //   K = P H^T (H P H^T / R + I)^{-1} / R ;  K_h = K h ;  K_x = K H
-        // the m (< 23) Jacobian rows are rebuilt, in point order, from what k_measure left per point
+        // the m (< 23) Jacobian rows are rebuilt, in point order, from what k_residual left per point
         if (tid == 0) {
             int mrows = 0;
             for (int q = sc.q_begin; q < sc.q_end && mrows < 22; q++) if (sc.selected[q]) S.row_idx[mrows++] = q;
@@ -533,12 +485,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(FilterCtl* ctl, const d
             double h[12]; double z;
             for (int a = 0; a < 12; a++) h[a] = 0.0;
             const int q = S.row_idx[tid];
-            if (ctl->extrinsic_est) jacobian_row<true>(ps, sc.body[q], sc.normvec[q], h, z);
+            if (extr) jacobian_row<true>(ps, sc.body[q], sc.normvec[q], h, z);
             else jacobian_row<false>(ps, sc.body[q], sc.normvec[q], h, z);
             for (int a = 0; a < 12; a++) S.rows[tid * 13 + a] = h[a];
             S.rows[tid * 13 + 12] = z;
         }
         __syncthreads();
+#pragma unroll 1
         for (int e = tid; e < n * mr; e += nt) {                 // PHt = P H^T  (23 x m)
             const int i = e / mr, r = e % mr;
             double v = 0.0;
@@ -547,6 +500,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(FilterCtl* ctl, const d
         }
         __syncthreads();
         const int ld = mr + 13;
+#pragma unroll 1
         for (int e = tid; e < mr * ld; e += nt) {                // [H P H^T / R + I | h_x | h]
             const int r = e / ld, c2 = e % ld;
             double v;
@@ -560,14 +514,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(FilterCtl* ctl, const d
             S.aug[r * ld + c2] = v;
         }
         __syncthreads();
-        ok = gj_eliminate(S.aug, mr, ld, ld, S.colbuf, S.row_of, S.used, &S.piv);
+        ok = gj_eliminate(S.aug, mr, ld, ld, S.row_of);
         if (ok) {
+#pragma unroll 1
             for (int e = tid; e < mr * 13; e += nt) {            // T = S^{-1} [h_x | h]
                 const int k = e / 13, j = e % 13;
                 const int pr = S.row_of[k];
                 S.T[e] = S.aug[pr * ld + mr + j] / S.aug[pr * ld + k];
             }
             __syncthreads();
+#pragma unroll 1
             for (int e = tid; e < n * 13; e += nt) {             // [K_x | K_h] = PHt T / R
                 const int i = e / 13, j = e % 13;
                 double v = 0.0;
@@ -578,135 +534,263 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(FilterCtl* ctl, const d
         }
     } else if (solver == 0) {
         // -------------------------------------------------------------- information form exactly as the reference, esekfom.hpp:1782-1809
-        //   P_temp = (P/R)^{-1};  P_temp[0:12,0:12] += H^T H;  P_inv = P_temp^{-1}
+        //   P_temp = (P/R)^{-1} (S.L, from solve_prepare);  P_temp[0:12,0:12] += H^T H;  P_inv = P_temp^{-1}
+#pragma unroll 1
         for (int e = tid; e < n * 2 * n; e += nt) {
             const int i = e / (2 * n), j = e % (2 * n);
-            S.aug[e] = j < n ? S.P[i * n + j] / R : (j - n == i ? 1.0 : 0.0);
+            double v;
+            if (j < n) { v = S.L[i * n + j]; if (i < 12 && j < 12) v += S.HTH[i * 12 + j]; }
+            else v = (j - n == i) ? 1.0 : 0.0;
+            S.aug[e] = v;
         }
         __syncthreads();
-        ok = gj_eliminate(S.aug, n, 2 * n, 2 * n, S.colbuf, S.row_of, S.used, &S.piv);
+        ok = gj_eliminate(S.aug, n, 2 * n, 2 * n, S.row_of);
         if (ok) {
-            for (int e = tid; e < n * n; e += nt) {
-                const int k = e / n, j = e % n;
-                const int pr = S.row_of[k];
-                double v = S.aug[pr * 2 * n + n + j] / S.aug[pr * 2 * n + k];
-                if (k < 12 && j < 12) v += S.HTH[k * 12 + j];
-                S.L[e] = v;
-            }
-            __syncthreads();
-            for (int e = tid; e < n * 2 * n; e += nt) {
-                const int i = e / (2 * n), j = e % (2 * n);
-                S.aug[e] = j < n ? S.L[i * n + j] : (j - n == i ? 1.0 : 0.0);
-            }
-            __syncthreads();
-            ok = gj_eliminate(S.aug, n, 2 * n, 2 * n, S.colbuf, S.row_of, S.used, &S.piv);
-        }
-        if (ok) {
+            // P_inv[:, 0:12] first (one division per entry), then
             // K_h = P_inv[:, 0:12] H^T h ;  K_x[:, 0:12] = P_inv[:, 0:12] H^T H
+#pragma unroll 1
+            for (int e = tid; e < n * 12; e += nt) {
+                const int i = e / 12, a = e % 12;
+                const int pr = S.row_of[i];
+                S.L[i * 12 + a] = S.aug[pr * 2 * n + n + a] / S.aug[pr * 2 * n + i];
+            }
+            __syncthreads();
+#pragma unroll 1
             for (int e = tid; e < n * 13; e += nt) {
                 const int i = e / 13, j = e % 13;
-                const int pr = S.row_of[i];
-                const double piv = S.aug[pr * 2 * n + i];
                 double v = 0.0;
-                for (int a = 0; a < 12; a++) v += (S.aug[pr * 2 * n + n + a] / piv) * (j < 12 ? S.HTH[a * 12 + j] : S.Hth[a]);
+                for (int a = 0; a < 12; a++) v += S.L[i * 12 + a] * (j < 12 ? S.HTH[a * 12 + j] : S.Hth[a]);
                 if (j < 12) S.Kx[i * 12 + j] = v; else S.Kh[i] = v;
             }
         }
     } else {
-        // -------------------------------------------------------------- same gain through one 12x12 solve.
+        // -------------------------------------------------------------- the same gain through one small solve.
         // With A = P/R and E = [I_12; 0]:  (A^{-1} + E M E^T)^{-1} E = A E (I + M A_11)^{-1}, hence
         //   [K_h | K_x[:, 0:12]] = (P[:, 0:12] / R) (I + H^T H P_11 / R)^{-1} [H^T h | H^T H]
         // -- algebraically identical to esekfom.hpp:1782-1809 without the two 23x23 inversions.
-        const int ld = 25;
-        for (int e = tid; e < 12 * ld; e += nt) {
-            const int r = e / ld, c2 = e % ld;
-            double v;
-            if (c2 < 12) {
-                v = 0.0;
-                for (int k = 0; k < 12; k++) v += S.HTH[r * 12 + k] * (S.P[k * n + c2] / R);
-                v += (r == c2 ? 1.0 : 0.0);
-            } else if (c2 == 12) v = S.Hth[r];
-            else v = S.HTH[r * 12 + (c2 - 13)];
-            S.aug[e] = v;
+        // Rows/columns ne..11 of H^T H are zero when the extrinsic columns are (ne = 6): the system
+        // is then block upper-triangular and only its leading ne x ne block needs eliminating.
+        const int ld = ne + ne + 1;                       // <= 25 columns: one lane each
+        const double Rinv = 1.0 / R;
+        const int nwarps = nt >> 5;
+#pragma unroll 1
+        for (int r = warp; r < ne; r += nwarps) {
+            if (lane < ld) {
+                double v;
+                if (lane < ne) {
+                    v = 0.0;
+#pragma unroll 1
+                    for (int k = 0; k < ne; k++) v += S.HTH[r * 12 + k] * (S.P[k * n + lane] * Rinv);
+                    v += (r == lane ? 1.0 : 0.0);
+                } else if (lane == ne) v = S.Hth[r];
+                else v = S.HTH[r * 12 + (lane - ne - 1)];
+                S.aug[r * ld + lane] = v;
+            }
         }
         __syncthreads();
-        ok = gj_eliminate(S.aug, 12, ld, ld, S.colbuf, S.row_of, S.used, &S.piv);
+        if (warp == 0) { const bool w_ok = gj_warp(S.aug, ne, ld, ld, S.row_of, lane); if (lane == 0) S.m_rows = w_ok ? 1 : 0; }
+        __syncthreads();
+        ok = S.m_rows != 0;
         if (ok) {
-            for (int e = tid; e < 12 * 13; e += nt) {
-                const int k = e / 13, j = e % 13;
-                const int pr = S.row_of[k];
-                S.T[e] = S.aug[pr * ld + 12 + j] / S.aug[pr * ld + k];      // column 0: for H^T h, 1..12: for H^T H
+#pragma unroll 1
+            for (int k = warp; k < ne; k += nwarps) {
+                if (lane <= ne) {
+                    const int pr = S.row_of[k];
+                    S.T[k * 13 + lane] = S.aug[pr * ld + ne + lane] / S.aug[pr * ld + k];   // column 0: for H^T h, 1..ne: for H^T H
+                }
             }
             __syncthreads();
-            for (int e = tid; e < n * 13; e += nt) {
-                const int i = e / 13, j = e % 13;
-                double v = 0.0;
-                for (int a = 0; a < 12; a++) v += (S.P[i * n + a] / R) * S.T[a * 13 + j];
-                if (j == 0) S.Kh[i] = v; else S.Kx[i * 12 + (j - 1)] = v;
+#pragma unroll 1
+            for (int i = warp; i < n; i += nwarps) {
+                if (lane < 13) {
+                    double v = 0.0;
+                    if (lane <= ne) {
+#pragma unroll 1
+                        for (int a = 0; a < ne; a++) v += (S.P[i * n + a] * Rinv) * S.T[a * 13 + lane];
+                    }
+                    if (lane == 0) S.Kh[i] = v; else S.Kx[i * 12 + (lane - 1)] = v;
+                }
             }
         }
     }
     __syncthreads();
+    STAMP(4);
     if (!ok) {
         if (tid == 0) { ctl->error = 1; ctl->done = 1; ctl->n_pass = n_pass + 1; }
         return;
     }
-    // ------------------------------------------------------------------ esekfom.hpp:1815-1832
+    // ------------------------------------------------------------------ esekfom.hpp:1815-1817
     if (tid < n) {
         double v = S.Kh[tid];
+#pragma unroll 1
         for (int j = 0; j < 12; j++) v += S.Kx[tid * 12 + j] * S.dx_new[j];
-        S.dxu[tid] = v - S.dx_new[tid];                       // K_h + (K_x - I) dx_new
+        const double d = v - S.dx_new[tid];                   // K_h + (K_x - I) dx_new
+        S.dxu[tid] = d;
+        const unsigned over = __ballot_sync(0x7fffffu, fabs(d) > ctl->limit[tid]);
+        if (tid == 0) S.over = over ? 1 : 0;
     }
     __syncthreads();
+    STAMP(5);
+    // esekfom.hpp:1818-1834 (S.over is complete: it was written before the barrier above)
+    int converge = S.over ? 0 : 1;
+    int t = t_in;
+    if (converge) t++;
+    if (!t && it == max_iter - 2) converge = 1;               // T2: force a re-search on the last pass
+    const int finish = (t > 1 || it == max_iter - 1) ? 1 : 0;
+    // x_.boxplus(dx_) and -- only when this pass is the last -- the congruence blocks at dx_
+    // for the final covariance (esekfom.hpp:1817, 1836-1876)
+    if (lane == 0) {
+        if (warp < 2) {
+            const int idx = warp == 0 ? 3 : 6, xo = warp == 0 ? X_ROT : X_OFFR;
+            const D3 d = d3(S.dxu[idx], S.dxu[idx + 1], S.dxu[idx + 2]);
+            stq(S.xnew + xo, qmul(ldq(ctl->x + xo), so3_exp(d)));                                   // SOn.hpp:233-236
+            if (finish) {
+                const M33 J = transpose33(A_matrix(d));
+#pragma unroll 1
+                for (int i = 0; i < 9; i++) S.J[warp][i] = J.m[i];
+            }
+        } else if (warp == 2) {
+            const D3 g = S2_boxplus(ld3(ctl->x + X_GRAV), S.dxu[21], S.dxu[22]);
+            st3(S.xnew + X_GRAV, g);
+            if (finish) S2_congruence(g, ld3(ctl->x_prop + X_GRAV), S.dxu[21], S.dxu[22], S.M2);
+        }
+    }
+    if (warp == 3 && lane < 15) {
+        const int b = lane / 3, c = lane % 3;
+        const int dof = b == 0 ? 0 : 9 + 3 * (b - 1);
+        const int xo = b == 0 ? X_POS : (b == 1 ? X_OFFT : (b == 2 ? X_VEL : (b == 3 ? X_BG : X_BA)));
+        S.xnew[xo + c] = ctl->x[xo + c] + S.dxu[dof + c];                                           // vect.hpp:117-119
+    }
+    __syncthreads();
+    STAMP(6);
+    if (tid < XLEN) { ctl->x[tid] = S.xnew[tid]; if (lg) lg->x_after[tid] = S.xnew[tid]; }
     if (tid == 0) {
-        for (int i = 0; i < XLEN; i++) S.xnew[i] = ctl->x[i];
-        state_boxplus(S.xnew, S.dxu);
-        int converge = 1;
-        for (int i = 0; i < n; i++) if (fabs(S.dxu[i]) > ctl->limit[i]) { converge = 0; break; }
-        int t = t_in;
-        if (converge) t++;
-        if (!t && it == max_iter - 2) converge = 1;            // T2: force a re-search on the last pass
-        const int finish = (t > 1 || it == max_iter - 1) ? 1 : 0;
-        S.finish = finish;
-        for (int i = 0; i < XLEN; i++) ctl->x[i] = S.xnew[i];
         ctl->t = t;
         ctl->converge = converge;
         ctl->n_pass = n_pass + 1;
         ctl->iter = it + 1;
         if (finish) ctl->done = 1;
-        if (lg) { lg->converged = converge; for (int i = 0; i < XLEN; i++) lg->x_after[i] = S.xnew[i]; }
-        if (finish) make_congruence(S.dxu, S.xnew, ctl->x_prop, S.J, S.M2);
+        if (lg) lg->converged = converge;
     }
-    __syncthreads();
-    if (!S.finish) {
+    if (!finish) {
         // the reference leaves P_ = congruence-transformed P_propagated between passes
+#pragma unroll 1
         for (int e = tid; e < n * n; e += nt) ctl->P[e] = S.P[e];
+        STAMP(7);
         return;
     }
     // ------------------------------------------------------------------ final covariance, esekfom.hpp:1834-1927
+#pragma unroll 1
     for (int e = tid; e < n * n; e += nt) S.L[e] = S.P[e];
     __syncthreads();
     apply_rows(S.L, S.P, S.J[0], S.J[1], S.M2, n, n);          // L rows from P rows
     __syncthreads();
-    apply_rows(S.Kx, S.Kx, S.J[0], S.J[1], S.M2, 12, 12);      // K_x rows, first 12 columns
-    apply_cols(S.L, S.J[0], S.J[1], S.M2);
+    apply_rows(S.Kx, S.Kx, S.J[0], S.J[1], S.M2, 12, 12);      // K_x rows, first 12 columns  (threads 0..11)
+    apply_cols(S.L, S.J[0], S.J[1], S.M2, 32);                 // threads 32..54
+    apply_cols(S.P, S.J[0], S.J[1], S.M2, 64);                 // threads 64..86  (L rows no longer read P)
     __syncthreads();
-    apply_cols(S.P, S.J[0], S.J[1], S.M2);
-    __syncthreads();
+#pragma unroll 1
     for (int e = tid; e < n * n; e += nt) {                     // P_ = L_ - K_x[:, 0:12] P_[0:12, :]
         const int i = e / n, j = e % n;
         double v = 0.0;
+#pragma unroll 1
         for (int a = 0; a < 12; a++) v += S.Kx[i * 12 + a] * S.P[a * n + j];
         ctl->P[e] = S.L[e] - v;
     }
+    STAMP(7);
 }
 
-__global__ void k_init_ctl(FilterCtl* ctl) {
-    const int tid = threadIdx.x;
-    for (int e = tid; e < NDOF * NDOF; e += blockDim.x) ctl->P_prop[e] = ctl->P[e];
-    if (tid < XLEN) ctl->x_prop[tid] = ctl->x[tid];
-    if (tid == 0) { ctl->iter = -1; ctl->t = 0; ctl->converge = 1; ctl->done = 0; ctl->n_pass = 0; ctl->error = 0; }
+// k_residual -- everything of h_share_model after the search (laserMapping.cpp:674-752), one
+// thread per scan point, every pass: plane fit on the cached neighbours, gating, Jacobian row;
+// the rows never reach memory -- they are folded into the FP64 normal equations with warp
+// shuffles and one deterministic partial per block.
+//
+// Block 0 is the solver block: it owns no scan points.  While the other blocks work it runs the
+// H-independent half of the Kalman step (solve_prepare), then waits for their tickets, reduces
+// the partials in a fixed order and
+//   mode 0: finishes the Kalman step of this pass on the spot (single GPU -- no extra launch),
+//   mode 1: publishes the 92 sums for the all-reduce across ranks (k_solve_only follows).
+// Waiting cannot deadlock: block 0 holds no resource another block needs in order to run.
+template <bool EXTR>
+__global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterCtl* ctl, double* __restrict__ partials,
+                                                             double* red_g, int mode, PassLog* logs, int solver) {
+    __shared__ SolveShared S;
+    if (ctl->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = RESID_THREADS / 32;
+    const int nwork = (int)gridDim.x - 1;
+    if (blockIdx.x > 0) {
+        const int wb = (int)blockIdx.x - 1;
+        const PoseS s = load_pose(ctl->x);
+        double acc[3] = {0.0, 0.0, 0.0};
+        const int q0 = sc.q_begin, q1 = sc.q_end;
+        for (int base = q0 + wb * RESID_THREADS + warp * 32; base < q1; base += nwork * RESID_THREADS) {
+            const int q = base + lane;
+            double h[12]; double z = 0.0; float ar = 0.f;
+            bool contrib = false;
+            if (q < q1) contrib = measure_point<EXTR>(sc, q, s, h, z, ar);
+            warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane);
+        }
+        double (*wacc)[PSTRIDE] = reinterpret_cast<double (*)[PSTRIDE]>(S.aug);     // NW x 96 doubles of scratch
+#pragma unroll
+        for (int j = 0; j < 3; j++) wacc[warp][lane + 32 * j] = acc[j];
+        __syncthreads();
+        if (threadIdx.x < PSTRIDE) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) v += wacc[w][threadIdx.x];
+            partials[(size_t)wb * PSTRIDE + threadIdx.x] = v;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(&ctl->ticket, 1);
+        return;
+    }
+    // ------------------------------------------------------------------ solver block
+    STAMP(0);
+    if (mode == 0) solve_prepare(S, ctl, solver);
+    STAMP(8);
+    if (threadIdx.x == 0) {
+        while (atomicAdd(&ctl->ticket, 0) < nwork) __nanosleep(64);
+        ctl->ticket = 0;
+    }
+    __syncthreads();
+    __threadfence();
+    STAMP(9);
+    {   // fixed-order reduction of the block partials: warp w takes rows w, w+NW, ...; lanes take outputs
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll 8
+        for (int b = warp; b < nwork; b += NW) {
+            const double* row = partials + (size_t)b * PSTRIDE;
+            a0 += __ldcg(&row[lane]); a1 += __ldcg(&row[lane + 32]); a2 += __ldcg(&row[lane + 64]);
+        }
+        double (*wacc)[PSTRIDE] = reinterpret_cast<double (*)[PSTRIDE]>(S.wred);
+        wacc[warp][lane] = a0; wacc[warp][lane + 32] = a1; wacc[warp][lane + 64] = a2;
+        __syncthreads();
+        if (threadIdx.x < PSTRIDE) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) v += wacc[w][threadIdx.x];
+            S.red[threadIdx.x] = v;
+            if (mode == 1 && threadIdx.x < NRED) red_g[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+    if (mode == 1) return;
+    solve_finish(S, ctl, sc, logs, solver);
 }
+
+// multi-GPU: the Kalman step from the all-reduced sums
+__global__ void __launch_bounds__(RESID_THREADS) k_solve_only(FilterCtl* ctl, const double* __restrict__ red_g, ScanView sc,
+                                                              PassLog* logs, int solver) {
+    __shared__ SolveShared S;
+    if (ctl->done) return;
+    solve_prepare(S, ctl, solver);
+    if (threadIdx.x < NRED) S.red[threadIdx.x] = red_g[threadIdx.x];
+    __syncthreads();
+    solve_finish(S, ctl, sc, logs, solver);
+}
+#undef STAMP
 
 // ============================================================================= NCCL (lazy)
 struct NcclUniqueId { char internal[128]; };
@@ -755,26 +839,29 @@ Filter::~Filter() {
     cudaSetDevice(map_->device());
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     body_.release(); nearest_.release(); nearest_cnt_.release(); selected_.release(); normvec_.release();
-    partials_.release(); red_.release(); ctl_.release(); logs_.release();
+    partials_.release(); red_.release(); ctl_.release(); ctl0_.release(); logs_.release();
     if (h_ctl_) cudaFreeHost(h_ctl_);
 }
 
 int Filter::init() {
     FL_CUDA(cudaSetDevice(map_->device()));
     FL_CHECK(ctl_.reserve(sizeof(FilterCtl)));
+    FL_CHECK(ctl0_.reserve(sizeof(FilterCtl)));
     FL_CHECK(red_.reserve(sizeof(double) * PSTRIDE));
     FL_CHECK(logs_.reserve(sizeof(PassLog) * MAX_LOGS));
     FL_CUDA(cudaMallocHost(&h_ctl_, sizeof(FilterCtl)));
     memset(h_ctl_, 0, sizeof(FilterCtl));
     FL_CUDA(cudaMemsetAsync(ctl_.ptr, 0, sizeof(FilterCtl), stream()));
+    FL_CUDA(cudaMemsetAsync(ctl0_.ptr, 0, sizeof(FilterCtl), stream()));
     FL_CUDA(cudaMemsetAsync(logs_.ptr, 0, sizeof(PassLog) * MAX_LOGS, stream()));
-    // persistent grid: as many blocks as can be co-resident
-    int dev = map_->device(), sms = 0, occ_a = 0, occ_b = 0;
-    FL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, k_measure<false>, MEASURE_THREADS, 0));
-    FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_measure<true>, MEASURE_THREADS, 0));
-    grid_ = sms * std::max(1, std::min(occ_a, occ_b));
-    FL_CHECK(partials_.reserve(sizeof(double) * PSTRIDE * (size_t)grid_));
+    // k_search: as many co-resident blocks as fit (queries are spread over all of them);
+    // k_residual: one thread per point, at most max_resid_grid_ blocks (one partial row each)
+    int dev = map_->device(), occ = 0;
+    FL_CUDA(cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev));
+    FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search, SEARCH_THREADS, 0));
+    search_grid_max_ = sms_ * std::max(1, occ);
+    max_resid_grid_ = sms_;
+    FL_CHECK(partials_.reserve(sizeof(double) * PSTRIDE * (size_t)max_resid_grid_));
     FL_CHECK(reserve(std::max(1, max_points_)));
     return FL_OK;
 }
@@ -829,42 +916,70 @@ int Filter::set_shard(int q_begin, int q_end) {
 
 int Filter::upload_state(const double* x26, const double* P, double R) {
     FL_CUDA(cudaSetDevice(map_->device()));
-    memcpy(h_ctl_->x, x26, sizeof(double) * XLEN);
-    memcpy(h_ctl_->P, P, sizeof(double) * NDOF * NDOF);
-    for (int i = 0; i < NDOF; i++) h_ctl_->limit[i] = limit_[i];
-    h_ctl_->R = R;
-    h_ctl_->max_iter = max_iter_;
-    h_ctl_->extrinsic_est = extrinsic_est_;
-    // x, x_prop, P are contiguous with the header: copy [0, offsetof(P_prop))
-    FL_CUDA(cudaMemcpyAsync(ctl_.ptr, h_ctl_, offsetof(FilterCtl, P_prop), cudaMemcpyHostToDevice, stream()));
+    // what update_iterated_dyn_share_modified sets up before its loop (esekfom.hpp:1621-1631)
+    FilterCtl& c = *h_ctl_;
+    c.iter = -1; c.t = 0; c.converge = 1; c.done = 0; c.n_pass = 0; c.error = 0; c.ticket = 0; c.pad_ = 0;
+    c.max_iter = max_iter_;
+    c.extrinsic_est = extrinsic_est_;
+    c.R = R;
+    for (int i = 0; i < NDOF; i++) c.limit[i] = limit_[i];
+    memcpy(c.x, x26, sizeof(double) * XLEN);
+    memcpy(c.x_prop, x26, sizeof(double) * XLEN);                     // x_propagated = x_
+    memcpy(c.P, P, sizeof(double) * NDOF * NDOF);
+    memcpy(c.P_prop, P, sizeof(double) * NDOF * NDOF);                // P_propagated = P_
+    FL_CUDA(cudaMemcpyAsync(ctl_.ptr, h_ctl_, sizeof(FilterCtl), cudaMemcpyHostToDevice, stream()));
+    FL_CUDA(cudaMemcpyAsync(ctl0_.ptr, ctl_.ptr, sizeof(FilterCtl), cudaMemcpyDeviceToDevice, stream()));
+    return FL_OK;
+}
+
+int Filter::restore_state() {
+    FL_CUDA(cudaSetDevice(map_->device()));
+    FL_CUDA(cudaMemcpyAsync(ctl_.ptr, ctl0_.ptr, sizeof(FilterCtl), cudaMemcpyDeviceToDevice, stream()));
     return FL_OK;
 }
 
 int Filter::run_passes() {
     FL_CUDA(cudaSetDevice(map_->device()));
     if (scan_.q_end > scan_.Q) { set_last_error("shard exceeds the scan"); return FL_ERR_ARG; }
-    FilterCtl* ctl = ctl_.as<FilterCtl>();
-    cudaStream_t st = stream();
-    k_init_ctl<<<1, 256, 0, st>>>(ctl);
-    launches_ = 1;
-    const MapView& mv = map_->view();
+    launches_ = 0;
     for (int pass = 0; pass <= max_iter_; pass++) {
-        if (extrinsic_est_) k_measure<true><<<grid_, MEASURE_THREADS, 0, st>>>(mv, scan_, ctl, partials_.as<double>());
-        else k_measure<false><<<grid_, MEASURE_THREADS, 0, st>>>(mv, scan_, ctl, partials_.as<double>());
-        launches_++;
+        FL_CHECK(launch_search_only());
+        FL_CHECK(launch_residual_only());
+        launches_ += 2;
         if (nranks_ > 1) {
-            k_solve<<<1, SOLVE_THREADS, 0, st>>>(ctl, partials_.as<double>(), grid_, red_.as<double>(), 1, scan_, logs_.as<PassLog>(), solver_);
+            cudaStream_t st = stream();
             int rc = nccl_->AllReduce(red_.ptr, red_.ptr, NRED, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm_, st);
             if (rc != 0) { set_last_error("ncclAllReduce failed: %d", rc); return FL_ERR_NCCL; }
-            k_solve<<<1, SOLVE_THREADS, 0, st>>>(ctl, partials_.as<double>(), grid_, red_.as<double>(), 2, scan_, logs_.as<PassLog>(), solver_);
-            launches_ += 2;
-        } else {
-            k_solve<<<1, SOLVE_THREADS, 0, st>>>(ctl, partials_.as<double>(), grid_, red_.as<double>(), 0, scan_, logs_.as<PassLog>(), solver_);
+            k_solve_only<<<1, RESID_THREADS, 0, st>>>(ctl_.as<FilterCtl>(), red_.as<double>(), scan_, logs_.as<PassLog>(), solver_);
             launches_++;
         }
     }
     FL_CUDA(cudaGetLastError());
     return FL_OK;
+}
+
+int Filter::launch_search_only() {
+    FL_CUDA(cudaSetDevice(map_->device()));
+    const int nq = scan_.q_end - scan_.q_begin;
+    const int sgrid = std::max(1, std::min(search_grid_max_, (nq * 32 + SEARCH_THREADS - 1) / SEARCH_THREADS));
+    k_search<<<sgrid, SEARCH_THREADS, 0, stream()>>>(map_->view(), scan_, ctl_.as<FilterCtl>());
+    FL_CUDA(cudaGetLastError());
+    return FL_OK;
+}
+int Filter::launch_residual_only() {
+    FL_CUDA(cudaSetDevice(map_->device()));
+    const int nq = scan_.q_end - scan_.q_begin;
+    // worker blocks (one thread per point, grid-stride beyond max_resid_grid_ - 1 blocks) + the solver block 0
+    resid_grid_ = std::min(max_resid_grid_ - 1, (nq + RESID_THREADS - 1) / RESID_THREADS) + 1;
+    const int mode = nranks_ > 1 ? 1 : 0;
+    if (extrinsic_est_) k_residual<true><<<resid_grid_, RESID_THREADS, 0, stream()>>>(scan_, ctl_.as<FilterCtl>(), partials_.as<double>(), red_.as<double>(), mode, logs_.as<PassLog>(), solver_);
+    else k_residual<false><<<resid_grid_, RESID_THREADS, 0, stream()>>>(scan_, ctl_.as<FilterCtl>(), partials_.as<double>(), red_.as<double>(), mode, logs_.as<PassLog>(), solver_);
+    FL_CUDA(cudaGetLastError());
+    return FL_OK;
+}
+int Filter::launch_measure_only() {
+    FL_CHECK(launch_search_only());
+    return launch_residual_only();
 }
 
 int Filter::sync() {

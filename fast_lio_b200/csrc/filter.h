@@ -28,12 +28,15 @@ struct FilterCtl {
     int max_iter;        // maximum_iter
     int extrinsic_est;   // extrinsic_est_en (laserMapping.cpp:739)
     int error;           // device-side failure (singular system)
+    int ticket;          // k_residual: blocks finished so far (the last one reduces and solves)
+    int pad_;
     double R;            // LASER_POINT_COV passed as R
     double limit[NDOF];
     double x[XLEN];
     double x_prop[XLEN];
     double P[NDOF * NDOF];
     double P_prop[NDOF * NDOF];
+    long long prof[16];  // clock64() stamps of the last solve_pass (thread 0), for tuning
 };
 
 struct ScanView {
@@ -62,7 +65,11 @@ public:
     int upload_scan(const float* body_xyzi, int nq);
     int set_scan_device(const float4* d_body, int nq);
     int upload_state(const double* x26, const double* P, double R);
+    int restore_state();                               // device-side copy of the last uploaded state -> control block
     int run_passes();                                  // enqueue every pass on the stream (no sync)
+    int launch_measure_only();
+    int launch_search_only();
+    int launch_residual_only();
     int download_state(double* x26, double* P, int* n_pass);
     int sync();
 
@@ -89,9 +96,9 @@ private:
     int extrinsic_est_ = 0;
     int solver_ = 0;
     ScanView scan_;
-    DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, partials_, red_, ctl_, logs_;
+    DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, partials_, red_, ctl_, ctl0_, logs_;
     FilterCtl* h_ctl_ = nullptr;       // pinned staging
-    int grid_ = 0;
+    int sms_ = 0, search_grid_max_ = 0, max_resid_grid_ = 0, resid_grid_ = 1;
     int launches_ = 0;
     bool shard_set_ = false;
     // NCCL (resolved lazily with dlopen so that single-GPU use needs no NCCL at all)

@@ -14,8 +14,10 @@
 
 #ifdef __CUDACC__
 #define FL_HD __host__ __device__ __forceinline__
+#define FL_COLD __host__ __device__ __noinline__
 #else
 #define FL_HD inline
+#define FL_COLD
 #endif
 
 namespace fl {
@@ -81,17 +83,14 @@ FL_HD M33 qmat(const Q4& q) {                       // QuaternionBase::toRotatio
     return r;
 }
 
-// mtkmath.hpp:142-176
+// mtkmath.hpp:142-176  (Taylor branch verbatim; the sqrt/cos/sin branch is out of line)
+FL_COLD static void cos_sinc_exact(double x2, double& c, double& sinc) {
+    double x = sqrt(x2);
+    c = cos(x); sinc = sin(x) / x;
+}
 FL_HD void cos_sinc_sqrt(double x2, double& c, double& sinc) {
-    const double taylor_0_bound = 2.220446049250313e-16;            // epsilon<double>
-    const double taylor_2_bound = 1.4901161193847656e-08;            // sqrt(eps)
-    const double taylor_n_bound = 1.220703125e-04;                   // sqrt(sqrt(eps))
-    (void)taylor_0_bound; (void)taylor_2_bound;
-    if (x2 >= taylor_n_bound) {
-        double x = sqrt(x2);
-        c = cos(x); sinc = sin(x) / x;
-        return;
-    }
+    const double taylor_n_bound = 1.220703125e-04;                   // sqrt(sqrt(eps<double>))
+    if (x2 >= taylor_n_bound) { cos_sinc_exact(x2, c, sinc); return; }
     const double inv[7] = {1 / 3., 1 / 4., 1 / 5., 1 / 6., 1 / 7., 1 / 8., 1 / 9.};
     double cosi = 1., s = 1.;
     double term = -1 / 2. * x2;
@@ -112,20 +111,51 @@ FL_HD Q4 mtk_exp(const D3& v, double scale) {
     return r;
 }
 FL_HD Q4 so3_exp(const D3& v) { return mtk_exp(v, 0.5); }            // SOn.hpp:284-288
-FL_HD D3 so3_log(const Q4& q) {                                      // SOn.hpp:293-297 -> mtkmath.hpp:268-288 (T7)
+// Exact forms (transcendental calls) are kept out of line: the filter only ever sees small
+// tangent vectors, for which the series below are accurate to the last bits of FP64 and avoid
+// hundreds of cold instructions in the single-block solve.
+FL_COLD static D3 so3_log_exact(const Q4& q) {                       // SOn.hpp:293-297 -> mtkmath.hpp:268-288 (T7)
     D3 v = d3(q.x, q.y, q.z);
     double nv = norm3(v);
     if (nv < MTK_TOL) nv = MTK_TOL;
     double s = 2.0 / nv * atan(nv / q.w);
     return v * s;
 }
-FL_HD M33 A_matrix(const D3& v) {                                    // mtkmath.hpp:235-248
+FL_HD D3 so3_log(const Q4& q) {
+    // 2 atan(nv / w) / nv = (2 / w) * atan(r) / r,  r = nv / w;  atan(r)/r = 1 - r^2/3 + r^4/5 - ...
+    const double nv2 = q.x * q.x + q.y * q.y + q.z * q.z;
+    const double r2 = nv2 / (q.w * q.w);
+    if (!(r2 < 2.5e-3) || nv2 < MTK_TOL * MTK_TOL) return so3_log_exact(q);
+    double p = 1.0 / 17.0;
+    p = 1.0 / 15.0 - r2 * p; p = 1.0 / 13.0 - r2 * p; p = 1.0 / 11.0 - r2 * p; p = 1.0 / 9.0 - r2 * p;
+    p = 1.0 / 7.0 - r2 * p;  p = 1.0 / 5.0 - r2 * p;  p = 1.0 / 3.0 - r2 * p;  p = 1.0 - r2 * p;
+    return d3(q.x, q.y, q.z) * (2.0 / q.w * p);
+}
+FL_COLD static M33 A_matrix_exact(const D3& v) {                     // mtkmath.hpp:235-248
     double sq = v.x * v.x + v.y * v.y + v.z * v.z;
     double n = sqrt(sq);
     if (n < MTK_TOL) return eye33();
     M33 h = hat3(v), hh = mul33(h, h), r = eye33();
     double a = (1 - cos(n)) / sq, b = (1 - sin(n) / n) / sq;
     for (int i = 0; i < 9; i++) r.m[i] += a * h.m[i] + b * hh.m[i];
+    return r;
+}
+FL_HD M33 A_matrix(const D3& v) {
+    // (1 - cos n)/n^2 = 1/2 - n^2/24 + n^4/720 - ... ;  (1 - sin n / n)/n^2 = 1/6 - n^2/120 + n^4/5040 - ...
+    const double sq = v.x * v.x + v.y * v.y + v.z * v.z;
+    if (!(sq < 0.04)) return A_matrix_exact(v);
+    if (sq < MTK_TOL * MTK_TOL) return eye33();
+    double a = 1.0 / 87178291200.0;                       // 1/14!
+    a = 1.0 / 479001600.0 - sq * a; a = 1.0 / 3628800.0 - sq * a; a = 1.0 / 40320.0 - sq * a;
+    a = 1.0 / 720.0 - sq * a; a = 1.0 / 24.0 - sq * a; a = 0.5 - sq * a;
+    double b = 1.0 / 1307674368000.0;                     // 1/15!
+    b = 1.0 / 6227020800.0 - sq * b; b = 1.0 / 39916800.0 - sq * b; b = 1.0 / 362880.0 - sq * b;
+    b = 1.0 / 5040.0 - sq * b; b = 1.0 / 120.0 - sq * b; b = 1.0 / 6.0 - sq * b;
+    // hat(v)^2 = v v^T - |v|^2 I
+    M33 r;
+    r.m[0] = 1.0 + b * (v.x * v.x - sq); r.m[1] = -a * v.z + b * v.x * v.y;  r.m[2] = a * v.y + b * v.x * v.z;
+    r.m[3] = a * v.z + b * v.x * v.y;    r.m[4] = 1.0 + b * (v.y * v.y - sq); r.m[5] = -a * v.x + b * v.y * v.z;
+    r.m[6] = -a * v.y + b * v.x * v.z;   r.m[7] = a * v.x + b * v.y * v.z;   r.m[8] = 1.0 + b * (v.z * v.z - sq);
     return r;
 }
 
@@ -147,19 +177,34 @@ FL_HD D3 S2_boxplus(const D3& v, double d0, double d1) {              // S2.hpp:
     D3 Bu = d3(B[0] * d0 + B[1] * d1, B[2] * d0 + B[3] * d1, B[4] * d0 + B[5] * d1);
     return mul33v(qmat(mtk_exp(Bu, 0.5)), v);
 }
+FL_COLD static double s2_theta_over_sin_exact(double v_sin2, double v_cos) {
+    const double v_sin = sqrt(v_sin2);
+    return atan2(v_sin, v_cos) / v_sin;
+}
 FL_HD void S2_boxminus(const D3& self, const D3& other, double& r0, double& r1) {   // S2.hpp:144-167
-    double v_sin = norm3(mul33v(hat3(self), other));
-    double v_cos = dot3(self, other);
-    double theta = atan2(v_sin, v_cos);
-    if (v_sin < MTK_TOL) {
-        if (fabs(theta) > MTK_TOL) { r0 = 3.1415926; r1 = 0; } else { r0 = 0; r1 = 0; }
-    } else {
-        double B[6]; S2_Bx(other, B);
-        D3 hv = mul33v(hat3(other), self);
-        double f = theta / v_sin;
-        r0 = f * (B[0] * hv.x + B[2] * hv.y + B[4] * hv.z);
-        r1 = f * (B[1] * hv.x + B[3] * hv.y + B[5] * hv.z);
+    const D3 cr = mul33v(hat3(self), other);
+    const double v_sin2 = dot3(cr, cr);
+    const double v_cos = dot3(self, other);
+    if (v_sin2 < MTK_TOL * MTK_TOL) {
+        // theta = atan2(v_sin, v_cos) is 0 for aligned and pi for opposed vectors
+        if (v_cos < 0.0) { r0 = 3.1415926; r1 = 0; } else { r0 = 0; r1 = 0; }
+        return;
     }
+    // theta / v_sin = atan(t) / (t v_cos),  t = v_sin / v_cos
+    double f;
+    const double t2 = v_sin2 / (v_cos * v_cos);
+    if (v_cos > 0.0 && t2 < 2.5e-3) {
+        double p = 1.0 / 17.0;
+        p = 1.0 / 15.0 - t2 * p; p = 1.0 / 13.0 - t2 * p; p = 1.0 / 11.0 - t2 * p; p = 1.0 / 9.0 - t2 * p;
+        p = 1.0 / 7.0 - t2 * p;  p = 1.0 / 5.0 - t2 * p;  p = 1.0 / 3.0 - t2 * p;  p = 1.0 - t2 * p;
+        f = p / v_cos;
+    } else {
+        f = s2_theta_over_sin_exact(v_sin2, v_cos);
+    }
+    double B[6]; S2_Bx(other, B);
+    const D3 hv = mul33v(hat3(other), self);
+    r0 = f * (B[0] * hv.x + B[2] * hv.y + B[4] * hv.z);
+    r1 = f * (B[1] * hv.x + B[3] * hv.y + B[5] * hv.z);
 }
 FL_HD void S2_Nx_yy(const D3& v, double N[6]) {                       // 2x3, S2.hpp:262-267
     double B[6]; S2_Bx(v, B);

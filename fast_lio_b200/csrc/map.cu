@@ -40,44 +40,128 @@ void DeviceBuffer::release() {
 enum Counter { C_LEAF_USED = 0, C_DELETED, C_ADDED, C_GROUPS, C_NINSERT, C_TOMB, C_ERROR, C_COMPACT, C_COUNT = 16 };
 
 // ============================================================================= kernels
-__global__ void k_morton_keys(const float4* __restrict__ src, int n, unsigned long long* __restrict__ keys,
-                              unsigned* __restrict__ vals) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        float4 p = src[i];
-        keys[i] = morton_key(p.x, p.y, p.z);
-        vals[i] = (unsigned)i;
-    }
+// ----------------------------------------------------------------------------- k-d partition build
+// Top-down, level-synchronous: every level (1) bounds each segment, (2) sorts all points by
+// (segment, coordinate on the segment's longest axis) with one radix sort, (3) splits each
+// segment at a leaf boundary.  A segment owns a contiguous range of sorted points [p0, p1) and a
+// contiguous range of leaves [a, b); splits are placed on 32^k-aligned leaf boundaries so that
+// the five binary levels below any 32-wide node are exactly its children.
+struct Segment { int p0, p1, a, b; };
+
+__device__ __forceinline__ unsigned flip_float(float f) {
+    const unsigned u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+// split leaf of a segment covering leaves [a, b), b - a >= 2
+__host__ __device__ __forceinline__ int split_leaf(int a, int b) {
+    const int span = b - a;
+    long long p = 1;
+    while (p * FAN < span) p *= FAN;
+    const int nch = (int)((span + p - 1) / p);
+    return a + (int)((nch / 2) * p);
 }
 
-// Scatter the Morton-sorted points into leaf buckets (`fill` points per leaf), clear the
-// remaining slots and the whole overflow pool, reset the chains.
-__global__ void k_fill_leaves(MapView m, const float4* __restrict__ src, const unsigned long long* __restrict__ keys,
-                              const unsigned* __restrict__ vals, int n, int fill) {
+__global__ void k_kd_init(int n, unsigned* __restrict__ idx, int* __restrict__ segid, Segment* seg, int n_leaves) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { idx[i] = (unsigned)i; segid[i] = 0; }
+    if (i == 0) { seg[0].p0 = 0; seg[0].p1 = n; seg[0].a = 0; seg[0].b = n_leaves; }
+}
+__global__ void k_kd_bbox_init(float* __restrict__ bbox, int nseg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nseg * 6) bbox[i] = (i % 6) < 3 ? INFINITY : -INFINITY;
+}
+__global__ void k_kd_bbox(const float4* __restrict__ src, const unsigned* __restrict__ idx, const int* __restrict__ segid,
+                          int n, float* __restrict__ bbox) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool live = r < n;
+    int s = -1;
+    float v[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (live) {
+        s = segid[r];
+        const float4 p = src[idx[r]];
+        v[0] = v[3] = p.x; v[1] = v[4] = p.y; v[2] = v[5] = p.z;
+    }
+    // positions are ordered by segment: usually the whole warp shares one segment
+    const int s0 = __shfl_sync(FULL, s, 0);
+    if (__all_sync(FULL, s == s0)) {
+        if (s0 < 0) return;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                v[a] = fminf(v[a], __shfl_xor_sync(FULL, v[a], o));
+                v[3 + a] = fmaxf(v[3 + a], __shfl_xor_sync(FULL, v[3 + a], o));
+            }
+        }
+        if (lane < 3) atomic_min_float(&bbox[s0 * 6 + lane], lane == 0 ? v[0] : (lane == 1 ? v[1] : v[2]));
+        else if (lane < 6) atomic_max_float(&bbox[s0 * 6 + lane], lane == 3 ? v[3] : (lane == 4 ? v[4] : v[5]));
+    } else if (live) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { atomic_min_float(&bbox[s * 6 + a], v[a]); atomic_max_float(&bbox[s * 6 + 3 + a], v[3 + a]); }
+    }
+}
+__global__ void k_kd_keys(const float4* __restrict__ src, const unsigned* __restrict__ idx, const int* __restrict__ segid, int n,
+                          const float* __restrict__ bbox, unsigned long long* __restrict__ keys, unsigned* __restrict__ vals) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int s = segid[r];
+    const float* b = &bbox[s * 6];
+    // longest axis, first one wins ties (ikd_Tree.cpp:704-707)
+    const float ex = b[3] - b[0], ey = b[4] - b[1], ez = b[5] - b[2];
+    int axis = 0; float best = ex;
+    if (ey > best) { best = ey; axis = 1; }
+    if (ez > best) { axis = 2; }
+    const unsigned id = idx[r];
+    const float4 p = src[id];
+    const float c = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+    keys[r] = ((unsigned long long)(unsigned)s << 32) | flip_float(c);
+    vals[r] = id;
+}
+__global__ void k_kd_split(const Segment* __restrict__ in, Segment* __restrict__ out, int nseg, int fill) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const Segment g = in[s];
+    Segment l = g, r;
+    r.p0 = r.p1 = g.p1; r.a = r.b = g.b;
+    if (g.b - g.a >= 2) {
+        const int m = split_leaf(g.a, g.b);
+        long long cut = (long long)g.p0 + (long long)(m - g.a) * fill;
+        if (cut > g.p1) cut = g.p1;
+        l.p1 = (int)cut; l.b = m;
+        r.p0 = (int)cut; r.p1 = g.p1; r.a = m; r.b = g.b;
+    }
+    out[2 * s] = l;
+    out[2 * s + 1] = r;
+}
+__global__ void k_kd_assign(const unsigned long long* __restrict__ sorted_keys, int n, const Segment* __restrict__ next_seg,
+                            int* __restrict__ segid) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int s = (int)(sorted_keys[r] >> 32);
+    segid[r] = 2 * s + (r >= next_seg[2 * s].p1 ? 1 : 0);
+}
+
+// Scatter the partitioned points into their leaf buckets; clear every other slot, the overflow
+// pool and the chains.
+__global__ void k_clear_leaves(MapView m) {
     const long long total = (long long)m.leaf_cap * LEAF;
     for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < total;
          slot += (long long)gridDim.x * blockDim.x) {
-        const int leaf = (int)(slot / LEAF), s = (int)(slot % LEAF);
-        float4 out = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-        float pay = 0.f;
-        if (leaf < m.n_main && s < fill) {
-            const long long r = (long long)leaf * fill + s;
-            if (r < n) {
-                const float4 p = src[vals[r]];
-                out = make_float4(p.x, p.y, p.z, __int_as_float(1));
-                pay = p.w;
-            }
-        }
-        m.pts[slot] = out;
-        m.payload[slot] = pay;
-        if (s == 0) {
-            m.next[leaf] = -1;
-            if (leaf < m.n_main) {
-                const long long r0 = (long long)leaf * fill;
-                m.esep[0][leaf] = (leaf == 0 || r0 >= n) ? (leaf == 0 ? 0ull : ~0ull) : keys[r0];
-            }
-        }
+        m.pts[slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        m.payload[slot] = 0.f;
+        if ((slot % LEAF) == 0) m.next[slot / LEAF] = -1;
     }
+}
+__global__ void k_fill_leaves(MapView m, const float4* __restrict__ src, const unsigned* __restrict__ idx,
+                              const int* __restrict__ segid, const Segment* __restrict__ seg, int n) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const Segment g = seg[segid[r]];
+    const float4 p = src[idx[r]];
+    const long long slot = (long long)g.a * LEAF + (r - g.p0);
+    m.pts[slot] = make_float4(p.x, p.y, p.z, __int_as_float(1));
+    m.payload[slot] = p.w;
 }
 
 // One warp per main leaf: AABB of the valid points of the leaf and of its overflow chain.
@@ -108,7 +192,7 @@ __global__ void k_refit_leaves(MapView m) {
     }
 }
 
-// One warp per entity of level k (k >= 1): union of its <= 32 children boxes, first child's separator.
+// One warp per entity of level k (k >= 1): union of its <= 32 children boxes.
 __global__ void k_refit_level(MapView m, int k) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -128,7 +212,6 @@ __global__ void k_refit_level(MapView m, int k) {
         if (lane == 0) {
             m.ebox[k][2 * e] = make_float4(lx, ly, lz, 0.f);
             m.ebox[k][2 * e + 1] = make_float4(hx, hy, hz, 0.f);
-            m.esep[k][e] = m.esep[k - 1][e * FAN];
         }
     }
 }
@@ -143,18 +226,12 @@ __global__ void __launch_bounds__(256) k_knn_batch(MapView m, const float4* __re
         const float4 qq = __ldg(&q[i]);
         KBest kb;
         knn_query(m, qq.x, qq.y, qq.z, kb, lane);
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < KNN_K; j++) cnt += (kb.idx[j] >= 0 && j < k) ? 1 : 0;
-        // lane j fetches neighbour j
-        int myidx = -1; float myd = INFINITY;
-#pragma unroll
-        for (int j = 0; j < KNN_K; j++) if (lane == j) { myidx = kb.idx[j]; myd = kb.d[j]; }
+        const int cnt = min(k, __popc(__ballot_sync(FULL, lane < KNN_K && kb.idx >= 0)));
         if (lane < k) {
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (myidx >= 0) { p = m.pts[myidx]; p.w = m.payload[myidx]; }
+            if (kb.idx >= 0) { p = m.pts[kb.idx]; p.w = m.payload[kb.idx]; }
             out_pts[(size_t)i * k + lane] = p;
-            out_d2[(size_t)i * k + lane] = myd;
+            out_d2[(size_t)i * k + lane] = kb.d;
         }
         if (lane == 0) out_cnt[i] = cnt;
     }
@@ -332,7 +409,7 @@ __global__ void __launch_bounds__(256) k_downsample_resolve(MapView m, const flo
     }
 }
 
-// One warp per new point: descend the separators to the home leaf, claim a free slot there or
+// One warp per new point: descend towards the nearest child box to the home leaf, claim a free slot there or
 // in its overflow chain (allocating a chain leaf from the pool if needed), publish the point
 // and grow the AABBs on the root path with float atomics ("partial refit").
 __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restrict__ pts, int n, int* counters) {
@@ -340,14 +417,18 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
         const float4 p = pts[i];
-        const unsigned long long key = morton_key(p.x, p.y, p.z);
         int node = 0;
         for (int k = m.n_levels - 1; k >= 0; k--) {
             const int e = node * FAN + lane;
-            const unsigned long long sep = (e < m.count[k]) ? m.esep[k][e] : ~0ull;
-            const unsigned mask = __ballot_sync(FULL, sep <= key);
-            const int c = mask ? (__popc(mask) - 1) : 0;
-            node = node * FAN + c;
+            unsigned key = 0xffffffffu;
+            if (e < m.count[k]) {
+                const float4 lo = m.ebox[k][2 * e], hi = m.ebox[k][2 * e + 1];
+                // empty entities have inverted boxes (distance +inf): they are the last resort
+                const float d = box_dist3(p.x, p.y, p.z, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+                key = (min(__float_as_uint(d), 0x7f800000u) & ~31u) | (unsigned)lane;
+            }
+            const unsigned best = __reduce_min_sync(FULL, key);
+            node = node * FAN + (int)(best & 31u);
         }
         const int home = node;
         int leaf = home;
@@ -410,7 +491,8 @@ Map::Map(int device, float downsample_size) : device_(device), downsample_(downs
 Map::~Map() {
     cudaSetDevice(device_);
     pts_.release(); payload_.release(); next_.release(); counters_.release();
-    for (int k = 0; k < MAX_LEVELS; k++) { ebox_[k].release(); esep_[k].release(); }
+    for (int k = 0; k < MAX_LEVELS; k++) ebox_[k].release();
+    segid_.release(); segtab_[0].release(); segtab_[1].release(); bbox_.release();
     src_.release(); keys_in_.release(); keys_out_.release(); vals_in_.release(); vals_out_.release();
     cub_tmp_.release(); scratch_.release(); scratch2_.release(); scratch3_.release();
     if (h_counters_) cudaFreeHost(h_counters_);
@@ -423,7 +505,6 @@ int Map::init() {
     FL_CHECK(counters_.reserve(sizeof(int) * C_COUNT));
     FL_CUDA(cudaMemsetAsync(counters_.ptr, 0, sizeof(int) * C_COUNT, stream_));
     FL_CUDA(cudaMallocHost(&h_counters_, sizeof(int) * C_COUNT));
-    v_.n_leaf_used = counters_.as<int>();
     // an empty map: one empty leaf under a one-level root, so that every kernel is well defined
     FL_CHECK(src_.reserve(sizeof(float4)));
     return build_from_sorted(src_.as<float4>(), 0);
@@ -450,9 +531,7 @@ int Map::ensure_capacity(int n_points) {
     while (true) {
         const int c = v_.count[k];
         FL_CHECK(ebox_[k].reserve(sizeof(float4) * 2 * (size_t)c));
-        FL_CHECK(esep_[k].reserve(sizeof(unsigned long long) * (size_t)c));
         v_.ebox[k] = ebox_[k].as<float4>();
-        v_.esep[k] = esep_[k].as<unsigned long long>();
         const int up = (c + FAN - 1) / FAN;
         k++;
         v_.count[k] = up;
@@ -472,26 +551,54 @@ int Map::refit() {
     return FL_OK;
 }
 
+static int kd_depth(int span) {
+    if (span <= 1) return 0;
+    const int m = split_leaf(0, span);
+    return 1 + std::max(kd_depth(m), kd_depth(span - m));
+}
+
 // d_src: n points (x, y, z, intensity) on the device, any order.
 int Map::build_from_sorted(const float4* d_src, int n) {
     FL_CUDA(cudaSetDevice(device_));
     FL_CHECK(ensure_capacity(n));
+    k_clear_leaves<<<blocks_for((long long)v_.leaf_cap * LEAF, 256), 256, 0, stream_>>>(v_);
     if (n > 0) {
+        const int L = v_.n_main;
+        const int depth = kd_depth(L);
+        const size_t max_seg = (size_t)1 << depth;
         FL_CHECK(keys_in_.reserve(sizeof(unsigned long long) * (size_t)n));
         FL_CHECK(keys_out_.reserve(sizeof(unsigned long long) * (size_t)n));
         FL_CHECK(vals_in_.reserve(sizeof(unsigned) * (size_t)n));
         FL_CHECK(vals_out_.reserve(sizeof(unsigned) * (size_t)n));
-        k_morton_keys<<<blocks_for(n, 256, 1 << 30), 256, 0, stream_>>>(d_src, n, keys_in_.as<unsigned long long>(), vals_in_.as<unsigned>());
-        size_t tmp = 0;
-        FL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in_.as<unsigned long long>(), keys_out_.as<unsigned long long>(),
-                                                vals_in_.as<unsigned>(), vals_out_.as<unsigned>(), n, 0, 63, stream_));
-        FL_CHECK(cub_tmp_.reserve(tmp));
-        tmp = cub_tmp_.bytes;
-        FL_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.ptr, tmp, keys_in_.as<unsigned long long>(), keys_out_.as<unsigned long long>(),
-                                                vals_in_.as<unsigned>(), vals_out_.as<unsigned>(), n, 0, 63, stream_));
+        FL_CHECK(segid_.reserve(sizeof(int) * (size_t)n));
+        FL_CHECK(segtab_[0].reserve(sizeof(Segment) * max_seg));
+        FL_CHECK(segtab_[1].reserve(sizeof(Segment) * max_seg));
+        FL_CHECK(bbox_.reserve(sizeof(float) * 6 * max_seg));
+        unsigned* idx = vals_out_.as<unsigned>();          // current order of the points
+        unsigned* idx_tmp = vals_in_.as<unsigned>();
+        int* segid = segid_.as<int>();
+        const int nb = blocks_for(n, 256, 1 << 30);
+        k_kd_init<<<nb, 256, 0, stream_>>>(n, idx, segid, segtab_[0].as<Segment>(), L);
+        int cur = 0;
+        for (int lvl = 0; lvl < depth; lvl++) {
+            const int nseg = 1 << lvl;
+            k_kd_bbox_init<<<blocks_for((long long)nseg * 6, 256, 1 << 30), 256, 0, stream_>>>(bbox_.as<float>(), nseg);
+            k_kd_bbox<<<nb, 256, 0, stream_>>>(d_src, idx, segid, n, bbox_.as<float>());
+            k_kd_keys<<<nb, 256, 0, stream_>>>(d_src, idx, segid, n, bbox_.as<float>(), keys_in_.as<unsigned long long>(), idx_tmp);
+            size_t tmp = 0;
+            const int end_bit = 32 + std::max(1, lvl);
+            FL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in_.as<unsigned long long>(), keys_out_.as<unsigned long long>(),
+                                                    idx_tmp, idx, n, 0, end_bit, stream_));
+            FL_CHECK(cub_tmp_.reserve(tmp));
+            tmp = cub_tmp_.bytes;
+            FL_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.ptr, tmp, keys_in_.as<unsigned long long>(), keys_out_.as<unsigned long long>(),
+                                                    idx_tmp, idx, n, 0, end_bit, stream_));
+            k_kd_split<<<blocks_for(nseg, 256, 1 << 30), 256, 0, stream_>>>(segtab_[cur].as<Segment>(), segtab_[cur ^ 1].as<Segment>(), nseg, fill_);
+            k_kd_assign<<<nb, 256, 0, stream_>>>(keys_out_.as<unsigned long long>(), n, segtab_[cur ^ 1].as<Segment>(), segid);
+            cur ^= 1;
+        }
+        k_fill_leaves<<<nb, 256, 0, stream_>>>(v_, d_src, idx, segid, segtab_[cur].as<Segment>(), n);
     }
-    k_fill_leaves<<<blocks_for((long long)v_.leaf_cap * LEAF, 256), 256, 0, stream_>>>(
-        v_, d_src, keys_out_.as<unsigned long long>(), vals_out_.as<unsigned>(), n, fill_);
     FL_CUDA(cudaGetLastError());
     h_counters_[C_LEAF_USED] = v_.n_main;
     FL_CUDA(cudaMemcpyAsync(&counters_.as<int>()[C_LEAF_USED], &h_counters_[C_LEAF_USED], sizeof(int), cudaMemcpyHostToDevice, stream_));

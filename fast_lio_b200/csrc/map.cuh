@@ -2,21 +2,23 @@
 //
 // The reference's ikd-Tree (include/ikd-Tree/ikd_Tree.{h,cpp}) is a pointer-chasing
 // binary k-d tree with 176-byte nodes (ikd_Tree.h:59-82) and ~33 dependent node visits
-// per query.  Here the map is a flattened, implicit 32-ary bounding-volume hierarchy:
+// per query.  Here the map is a flattened, implicit 32-ary bounding-volume hierarchy over
+// a k-d partition of the points:
 //
 //   level 0   leaf buckets: 32 slots of float4 (x, y, z, flag) = 512 B, one coalesced
-//             warp load; points sorted by Morton key at build time, `fill` slots
-//             populated, the rest left free for incremental inserts;
+//             warp load.  At (re)build time the points are split top-down at the median
+//             of the longest axis -- the rule of KD_TREE::BuildTree (ikd_Tree.cpp:679-733)
+//             -- until each cell holds `fill` points; the free slots absorb inserts.
 //   level k   entity e of level k (a leaf for k = 0, an internal node otherwise) has its
-//             AABB in ebox[k][e] (two float4: lo, hi) and its smallest Morton key in
-//             esep[k][e]; node j of level k+1 owns entities 32j .. 32j+31 of level k, so
-//             there are no child pointers at all and a warp tests all 32 children of a
-//             node with one box per lane.
+//             AABB in ebox[k][e] (two float4: lo, hi).  Node j of level k+1 owns entities
+//             32j .. 32j+31 of level k: five binary k-d levels collapse into one 32-wide
+//             node, there are no child pointers, and a warp tests all children of a node
+//             with one box per lane.
 //
-// A query is served by one warp: every lane holds the query, the running k-best list is
-// replicated in registers, candidates are ranked with a hardware warp reduction
-// (redux.sync) and the traversal state of each level lives in registers (the recursion
-// over the <= 7 levels is unrolled at compile time), so there is no stack in memory.
+// A query is served by one warp: every lane holds the query, the k best candidates live
+// one per lane (lanes 0..k-1, ascending), candidates are ranked with the hardware warp
+// reduction (redux.sync) and the traversal state of each level lives in registers (the
+// recursion over the <= 7 levels is unrolled at compile time): no stack in memory.
 #pragma once
 #include "common.cuh"
 
@@ -26,40 +28,34 @@ struct MapView {
     float4* pts;                     // [leaf_cap * 32]  (x, y, z, as_float(flag)); flag 1 = valid
     float* payload;                  // [leaf_cap * 32]  intensity of the point in that slot
     int* next;                       // [leaf_cap]       overflow chain of a leaf, -1 = none
-    float4* ebox[MAX_LEVELS];        // [padded count * 2] AABB (lo, hi) of each entity of level k
-    unsigned long long* esep[MAX_LEVELS];  // [padded count] smallest Morton key of the entity
+    float4* ebox[MAX_LEVELS];        // [count * 2]      AABB (lo, hi) of each entity of level k
     int count[MAX_LEVELS + 1];       // entities per level; count[n_levels] == 1 (the root)
     int n_levels;                    // number of internal levels (>= 1)
     int n_main;                      // leaves addressed by the implicit tree (== count[0])
     int leaf_cap;                    // allocated leaves (main + overflow pool)
-    int* n_leaf_used;                // device counter: main + allocated overflow leaves
 };
 
 __device__ __forceinline__ bool slot_valid(const float4& p) { return __float_as_int(p.w) == 1; }
 
 // ----------------------------------------------------------------------------- k-best list
-// Replicated in every lane; ascending by distance.  Mirrors MANUAL_HEAP + PointType_CMP
-// (ikd_Tree.h:93-201) in effect: a candidate enters only if strictly closer than the
-// current k-th best (ikd_Tree.cpp:1088).
+// Lane j < K holds the j-th best (distance, slot); other lanes hold +inf.  Mirrors MANUAL_HEAP
+// + PointType_CMP (ikd_Tree.h:93-201) in effect: a candidate enters only if strictly closer
+// than the current k-th best (ikd_Tree.cpp:1088); `w` caches that k-th best, warp-uniform.
 struct KBest {
-    float d[KNN_K];
-    int idx[KNN_K];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int i = 0; i < KNN_K; i++) { d[i] = INFINITY; idx[i] = -1; }
-    }
-    __device__ __forceinline__ float worst() const { return d[KNN_K - 1]; }
-    __device__ __forceinline__ void insert(float nd, int nidx) {
-        // branch-free sorted insert (nd < d[K-1] guaranteed by the caller)
-#pragma unroll
-        for (int i = KNN_K - 1; i > 0; i--) {
-            bool shift = nd < d[i - 1];
-            bool here = !shift && nd < d[i];
-            float dn = shift ? d[i - 1] : (here ? nd : d[i]);
-            int in = shift ? idx[i - 1] : (here ? nidx : idx[i]);
-            d[i] = dn; idx[i] = in;
+    float d;
+    int idx;
+    float w;
+    __device__ __forceinline__ void init() { d = INFINITY; idx = -1; w = INFINITY; }
+    // nd, nidx warp-uniform, nd < w
+    __device__ __forceinline__ void insert(float nd, int nidx, int lane) {
+        const float up_d = __shfl_up_sync(FULL, d, 1);
+        const int up_i = __shfl_up_sync(FULL, idx, 1);
+        if (lane < KNN_K && nd < d) {
+            const bool take_prev = lane > 0 && nd < up_d;
+            d = take_prev ? up_d : nd;
+            idx = take_prev ? up_i : nidx;
         }
-        if (nd < d[0]) { d[0] = nd; idx[0] = nidx; }
+        w = __shfl_sync(FULL, d, KNN_K - 1);
     }
 };
 
@@ -68,19 +64,16 @@ struct KBest {
 __device__ __forceinline__ void knn_leaf(const MapView& m, int leaf, float qx, float qy, float qz,
                                          KBest& kb, int lane) {
     while (leaf >= 0) {
-        const int slot = leaf * LEAF + lane;
-        const float4 p = __ldg(&m.pts[slot]);
+        const float4 p = __ldg(&m.pts[leaf * LEAF + lane]);
         const int nxt = __ldg(&m.next[leaf]);
         float d = slot_valid(p) ? sq_dist3(qx, qy, qz, p.x, p.y, p.z) : INFINITY;
-        // ascending extraction: after K extractions nothing left can beat the k-th best
 #pragma unroll 1
         for (int it = 0; it < KNN_K; it++) {
-            unsigned key = (d < kb.worst()) ? __float_as_uint(d) : 0xffffffffu;   // d >= 0: bits order like floats
-            unsigned best = __reduce_min_sync(FULL, key);
+            const unsigned key = (d < kb.w) ? __float_as_uint(d) : 0xffffffffu;   // d >= 0: bits order like floats
+            const unsigned best = __reduce_min_sync(FULL, key);
             if (best == 0xffffffffu) break;
-            unsigned who = __ballot_sync(FULL, key == best);
-            int src = __ffs(who) - 1;
-            kb.insert(__uint_as_float(best), leaf * LEAF + src);
+            const int src = __ffs(__ballot_sync(FULL, key == best)) - 1;
+            kb.insert(__uint_as_float(best), leaf * LEAF + src, lane);
             if (lane == src) d = INFINITY;
         }
         leaf = nxt;
@@ -89,7 +82,7 @@ __device__ __forceinline__ void knn_leaf(const MapView& m, int leaf, float qx, f
 
 // Visit node `node` of level L (its children are entities of level L-1).  Children are
 // taken nearest-first and re-tested against the shrinking k-th best distance after each
-// return -- the same pruning rule as KD_TREE::Search (ikd_Tree.cpp:1097-1243).
+// return -- the pruning rule of KD_TREE::Search (ikd_Tree.cpp:1097-1243).
 template <int L>
 __device__ __forceinline__ void knn_node(const MapView& m, int node, float qx, float qy, float qz,
                                          KBest& kb, int lane) {
@@ -103,8 +96,8 @@ __device__ __forceinline__ void knn_node(const MapView& m, int node, float qx, f
 #pragma unroll 1
     while (true) {
         // order by distance (low 5 mantissa bits traded for the lane id; pruning stays exact)
-        unsigned key = (di < kb.worst()) ? ((__float_as_uint(di) & ~31u) | (unsigned)lane) : 0xffffffffu;
-        unsigned best = __reduce_min_sync(FULL, key);
+        const unsigned key = (di < kb.w) ? ((__float_as_uint(di) & ~31u) | (unsigned)lane) : 0xffffffffu;
+        const unsigned best = __reduce_min_sync(FULL, key);
         if (best == 0xffffffffu) break;
         const int c = best & 31;
         if (lane == c) di = INFINITY;
@@ -141,8 +134,8 @@ __device__ __forceinline__ bool box_overlaps(const float4& lo, const float4& hi,
     return true;
 }
 
-// Functor interface: f.leaf(leaf_index) is called warp-uniformly for every leaf (main
-// leaves only; the functor walks the overflow chain itself) whose AABB overlaps the box.
+// Functor interface: f.leaf(leaf_index) is called warp-uniformly for every main leaf whose
+// AABB overlaps the box (the functor walks the overflow chain itself).
 template <int L, class F>
 __device__ __forceinline__ void box_node(const MapView& m, int node, const float* bmin, const float* bmax, F& f, int lane) {
     const int e = node * FAN + lane;

@@ -69,7 +69,8 @@ private:
     bool built_ = false;
 
     DeviceBuffer pts_, payload_, next_, counters_;
-    DeviceBuffer ebox_[MAX_LEVELS], esep_[MAX_LEVELS];
+    DeviceBuffer ebox_[MAX_LEVELS];
+    DeviceBuffer segid_, segtab_[2], bbox_;        // k-d partition build scratch
     DeviceBuffer src_, keys_in_, keys_out_, vals_in_, vals_out_, cub_tmp_, scratch_, scratch2_, scratch3_;
     int* h_counters_ = nullptr;     // pinned mirror of the device counters
 };

@@ -110,6 +110,8 @@ int fl_filter_sync(fl_filter_t* f);
 /* device time in milliseconds of `reps` back-to-back resident updates from the uploaded state
  * (CUDA events on the handle's stream); optionally flushes L2 between repetitions */
 int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_total);
+/* device time of `reps` launches of the dominant kernel alone (k_measure in search mode) */
+int fl_filter_time_search_pass(fl_filter_t* f, int reps, int flush_l2, float* ms_total);
 int fl_filter_gpu_launches(fl_filter_t* f);
 
 /* ------------------------------------------------------------------ multi-GPU (no reference counterpart)

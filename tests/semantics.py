@@ -1,0 +1,85 @@
+"""Pure-numpy restatement of the MAP-MUTATION semantics of the reference's ikd-Tree, used as a
+second, independent oracle next to oracle/_ref (test infrastructure only).
+
+  Add_Points(downsample_on=true)   include/ikd-Tree/ikd_Tree.cpp:478-548
+  Add_Points(downsample_on=false)  include/ikd-Tree/ikd_Tree.cpp:549-568
+  Delete_Point_Boxes               include/ikd-Tree/ikd_Tree.cpp:632-658 -> Delete_by_range :767-851
+"""
+import numpy as np
+
+F = np.float32
+
+
+class VoxelMapModel:
+    def __init__(self, pts4, ds=0.5):
+        self.ds = F(ds)
+        self.pts = [np.array(p, dtype=np.float32) for p in np.asarray(pts4, dtype=np.float32).reshape(-1, 4)]
+        self.valid = [True] * len(self.pts)
+        self.cells = {}
+        for i, p in enumerate(self.pts):
+            self.cells.setdefault(self._cell(p), []).append(i)
+
+    def _cell(self, p):
+        return tuple(float(np.floor(F(p[a]) / self.ds)) for a in range(3))
+
+    def _box(self, p):
+        bmin = np.array([F(np.floor(F(p[a]) / self.ds)) * self.ds for a in range(3)], dtype=np.float32)
+        bmax = (bmin + self.ds).astype(np.float32)
+        mid = np.array([F(float(bmin[a]) + float(F(bmax[a] - bmin[a])) / 2.0) for a in range(3)], dtype=np.float32)
+        return bmin, bmax, mid
+
+    @staticmethod
+    def _dist(a, b):
+        d = (a[:3] - b[:3]).astype(np.float32)
+        return F(F(F(d[0] * d[0]) + F(d[1] * d[1])) + F(d[2] * d[2]))
+
+    def _in_box(self, p, bmin, bmax):
+        return all(bmin[a] <= p[a] and bmax[a] > p[a] for a in range(3))
+
+    def _insert(self, p):
+        self.pts.append(np.array(p, dtype=np.float32))
+        self.valid.append(True)
+        self.cells.setdefault(self._cell(p), []).append(len(self.pts) - 1)
+
+    def add_points(self, batch4, downsample_on):
+        counter = 0
+        for p in np.asarray(batch4, dtype=np.float32).reshape(-1, 4):
+            if not downsample_on:
+                self._insert(p)
+                continue
+            bmin, bmax, mid = self._box(p)
+            storage = [i for i in self.cells.get(self._cell(p), []) if self.valid[i] and self._in_box(self.pts[i], bmin, bmax)]
+            min_dist = self._dist(p, mid)
+            result, result_is_new = p, True
+            for i in storage:
+                d = self._dist(self.pts[i], mid)
+                if d < min_dist:
+                    min_dist, result, result_is_new = d, self.pts[i].copy(), False
+            same = result_is_new or bool(np.all(np.abs(p[:3].astype(np.float64) - result[:3].astype(np.float64)) < 1e-6))
+            if len(storage) > 1 or same:
+                for i in storage:
+                    self.valid[i] = False
+                self._insert(result)
+                counter += 1
+        return counter
+
+    def delete_boxes(self, boxes6):
+        cnt = 0
+        for b in np.asarray(boxes6, dtype=np.float32).reshape(-1, 6):
+            for i, p in enumerate(self.pts):
+                if self.valid[i] and self._in_box(p, b[:3], b[3:]):
+                    self.valid[i] = False
+                    cnt += 1
+        return cnt
+
+    def flatten(self):
+        out = [p for p, v in zip(self.pts, self.valid) if v]
+        return np.array(out, dtype=np.float32).reshape(-1, 4)
+
+
+def sort_rows(a):
+    a = np.asarray(a, dtype=np.float32).reshape(-1, 4)
+    if len(a) == 0:
+        return a
+    order = np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))
+    return a[order]

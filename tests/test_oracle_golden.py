@@ -1,0 +1,123 @@
+"""CPU: the oracle against the committed golden vectors (tests/golden/*.npz, minted by
+tests/golden/make_golden.py from the reference's own ikd-Tree + the restatement) and against
+independent numpy formulations of its pieces."""
+import os
+
+import numpy as np
+import pytest
+
+from fast_lio_b200 import synth
+from oracle import bind
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def world_queries(pr):
+    q = np.zeros((len(pr.scan), 4), dtype=np.float32)
+    tmp = np.zeros(3, dtype=np.float32)
+    for i in range(len(pr.scan)):
+        bind.lib().oracle_transform_point(pr.x_prior, np.ascontiguousarray(pr.scan[i, :3]), tmp)
+        q[i, :3] = tmp
+    return q
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_generator_is_stable(problems, name):
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    pr = problems(name)
+    assert float(pr.map_pts.astype(np.float64).sum()) == float(g["map_sum"])
+    assert float(pr.scan.astype(np.float64).sum()) == float(g["scan_sum"])
+    assert np.array_equal(pr.x_prior, g["x_prior"])
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+@pytest.mark.parametrize("backend", ["port", "reference"])
+def test_knn_golden(problems, name, backend):
+    if backend == "reference" and not bind.have_ref():
+        pytest.skip("oracle/_ref not built")
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    pr = problems(name)
+    t = bind.KdTree(pr.map_pts, backend)
+    p, d, c = t.knn(world_queries(pr), 5)
+    assert np.array_equal(c, g["knn_cnt"]) and np.array_equal(d, g["knn_d2"]) and np.array_equal(p, g["knn_pts"])
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+@pytest.mark.parametrize("extr", [0, 1])
+def test_update_golden(problems, name, extr):
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    pr = problems(name)
+    t = bind.KdTree(pr.map_pts, "port")
+    o = bind.update_iterated(t, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, extr, nthreads=2)
+    assert np.array_equal(np.array([p["effct"] for p in o.passes]), g[f"effct_{extr}"])
+    assert np.array_equal(np.array([p["searched"] for p in o.passes]), g[f"searched_{extr}"])
+    assert np.array_equal(np.array([p["converged"] for p in o.passes]), g[f"converged_{extr}"])
+    assert np.allclose(np.stack([p["HtH"] for p in o.passes]), g[f"HtH_{extr}"], rtol=1e-12, atol=1e-9)
+    assert np.allclose(o.x, g[f"x_{extr}"], rtol=0, atol=1e-12)
+    assert np.allclose(o.P, g[f"P_{extr}"], rtol=1e-9, atol=1e-15)
+    assert np.array_equal(o.selected, g[f"selected_{extr}"])
+
+
+def test_update_reduces_error(problems):
+    pr = problems("small")
+    t = bind.KdTree(pr.map_pts, "port")
+    o = bind.update_iterated(t, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, 0)
+    assert np.abs(pr.x_prior[:3] - pr.x_true[:3]).max() > 0.02
+    assert np.abs(o.x[:3] - pr.x_true[:3]).max() < 5e-3
+    assert (np.diag(o.P)[:6] < np.diag(pr.P_prior)[:6]).all()
+    assert np.allclose(o.P, o.P.T, atol=1e-12)
+
+
+def test_esti_plane_against_lstsq():
+    """esti_plane (float32 column-pivoted QR) vs float64 least squares on well-conditioned planes."""
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = rng.normal(size=3); n /= np.linalg.norm(n)
+        d = rng.uniform(1.0, 5.0)
+        c = -d * n + rng.normal(size=3) * 0.0
+        u = np.cross(n, [1, 0, 0]); u /= np.linalg.norm(u); v = np.cross(n, u)
+        pts = np.array([c + rng.uniform(-1, 1) * u + rng.uniform(-1, 1) * v + rng.normal(0, 0.002) * n for _ in range(5)], dtype=np.float32)
+        ok, pabcd = bind.esti_plane(pts, 0.1)
+        sol, *_ = np.linalg.lstsq(pts.astype(np.float64), -np.ones(5), rcond=None)
+        nn = np.linalg.norm(sol)
+        ref = np.array([*(sol / nn), 1.0 / nn])
+        assert ok
+        assert np.allclose(pabcd, ref, atol=5e-4)
+    # points far off a plane are rejected
+    ok, _ = bind.esti_plane(np.array([[0, 0, 1], [1, 0, 1.5], [0, 1, 0.5], [1, 1, 1.9], [2, 2, 1]], dtype=np.float32), 0.1)
+    assert not ok
+
+
+def test_manifold_roundtrip():
+    """x [+] (y [-] x) == y for the compound state (boxplus/boxminus of vect, SO3, S2)."""
+    rng = np.random.default_rng(1)
+    L = bind.lib()
+    x = synth.true_state("avia")
+    for _ in range(50):
+        d = rng.normal(0, 0.02, 23)
+        y = x.copy()
+        L.oracle_state_boxplus(y, d)
+        back = np.zeros(23)
+        L.oracle_state_boxminus(y, x, back)
+        assert np.allclose(back, d, atol=1e-9)
+        assert abs(np.linalg.norm(y[23:26]) - synth.G_LEN) < 1e-9
+        assert abs(np.linalg.norm(y[3:7]) - 1.0) < 1e-3
+
+
+def test_inverse_matches_numpy():
+    rng = np.random.default_rng(2)
+    A = rng.normal(size=(23, 23)); A = A @ A.T + 23 * np.eye(23)
+    out = np.zeros((23, 23))
+    assert bind.lib().oracle_inverse(np.ascontiguousarray(A), out, 23) == 0
+    assert np.allclose(out, np.linalg.inv(A), rtol=1e-10, atol=1e-13)
+
+
+def test_A_matrix_matches_series():
+    L = bind.lib()
+    v = np.array([0.03, -0.02, 0.05])
+    out = np.zeros(9)
+    L.oracle_A_matrix(v, out)
+    K = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+    n = np.linalg.norm(v)
+    ref = np.eye(3) + (1 - np.cos(n)) / n**2 * K + (1 - np.sin(n) / n) / n**2 * K @ K
+    assert np.allclose(out.reshape(3, 3), ref, atol=1e-14)

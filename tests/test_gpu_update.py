@@ -66,3 +66,94 @@ def test_update_extrinsic_est(problems):
     o, (x, P, st, f) = run_both(pr, 0, extr=1)
     check_state(o, x, P)
     assert np.allclose(f.pass_logs()[0]["HtH"], o.passes[0]["HtH"], rtol=1e-9, atol=1e-6)
+
+
+def test_shard_equals_subscan(problems):
+    """Multi-GPU building block on one GPU: processing the shard [lo, hi) of a bound scan gives the
+    same normal equations as binding only scan[lo:hi] (what each rank contributes to the all-reduce)."""
+    pr = problems("small")
+    t = api.KdTree(0, 0.5)
+    t.Build(pr.map_pts)
+    n = len(pr.scan)
+    total = None
+    for rank in range(3):
+        lo, hi = api.shard_range(n, 3, rank)
+        fa = api.Esekf(t, max_points=n, max_iter=1)
+        fa.upload_scan(pr.scan); fa.set_shard(lo, hi); fa.upload_state(pr.x_prior, pr.P_prior, pr.R); fa.run()
+        fa.download_state()
+        fb = api.Esekf(t, max_points=n, max_iter=1)
+        fb.upload_scan(pr.scan[lo:hi]); fb.upload_state(pr.x_prior, pr.P_prior, pr.R); fb.run()
+        fb.download_state()
+        la, lb = fa.pass_logs()[0], fb.pass_logs()[0]
+        assert la["effct"] == lb["effct"]
+        assert np.array_equal(la["HtH"], lb["HtH"]) and np.array_equal(la["Hth"], lb["Hth"])
+        total = la["HtH"] if total is None else total + la["HtH"]
+    full = api.Esekf(t, max_points=n, max_iter=1)
+    full.upload_scan(pr.scan); full.upload_state(pr.x_prior, pr.P_prior, pr.R); full.run(); full.download_state()
+    assert np.allclose(total, full.pass_logs()[0]["HtH"], rtol=1e-12, atol=1e-9)
+
+
+def test_small_m_branch(problems):
+    """Fewer than 23 effective points -> the K = P H^T (H P H^T / R + I)^-1 / R branch (esekfom.hpp:1715-1744)."""
+    pr = problems("tiny")
+    scan = pr.scan[:14].copy()
+    ref_tree = bind.KdTree(pr.map_pts, "auto")
+    o = bind.update_iterated(ref_tree, scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, 0)
+    assert 0 < o.passes[0]["effct"] < 23
+    t = api.KdTree(0, 0.5); t.Build(pr.map_pts)
+    f = api.Esekf(t, max_points=64, max_iter=pr.cfg.max_iter)
+    x, P, _ = f.update_iterated_dyn_share_modified(scan, pr.x_prior, pr.P_prior, pr.R)
+    assert len(f.pass_logs()) == len(o.passes)
+    check_state(o, x, P)
+
+
+def test_no_effective_points_leaves_state_untouched(problems):
+    """effct_feat_num < 1 -> valid = false, every pass is skipped (laserMapping.cpp:708-713)."""
+    pr = problems("tiny")
+    far = pr.scan[:50].copy()
+    far[:, :3] += 5000.0                       # nothing within sqrt(5) m of any 5 map points
+    ref_tree = bind.KdTree(pr.map_pts, "auto")
+    o = bind.update_iterated(ref_tree, far, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, 0)
+    t = api.KdTree(0, 0.5); t.Build(pr.map_pts)
+    f = api.Esekf(t, max_points=64, max_iter=pr.cfg.max_iter)
+    x, P, _ = f.update_iterated_dyn_share_modified(far, pr.x_prior, pr.P_prior, pr.R)
+    assert np.array_equal(x, pr.x_prior) and np.array_equal(o.x, pr.x_prior)
+    assert np.allclose(P, o.P, rtol=0, atol=0)
+    logs = f.pass_logs()
+    assert len(logs) == len(o.passes) == pr.cfg.max_iter + 1
+    assert all(l["valid"] == 0 and l["effct"] == 0 for l in logs)
+
+
+def test_update_is_deterministic(problems):
+    pr = problems("small")
+    t = api.KdTree(0, 0.5); t.Build(pr.map_pts)
+    f = api.Esekf(t, max_points=len(pr.scan), max_iter=pr.cfg.max_iter)
+    a = f.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
+    b = f.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_full_size_properties(problems):
+    """BASELINE config 2 (30k points vs 1M-point map): size-independent checks -- the GPU kNN of a
+    sample against the port oracle, filter contraction towards the truth, symmetric P."""
+    pr = problems("velodyne_30k_1m")
+    t = api.KdTree(0, 0.5); t.Build(pr.map_pts)
+    f = api.Esekf(t, max_points=len(pr.scan), max_iter=pr.cfg.max_iter, solver=1)
+    x, P, _ = f.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
+    assert np.abs(x[:3] - pr.x_true[:3]).max() < 2e-3 < np.abs(pr.x_prior[:3] - pr.x_true[:3]).max()
+    assert np.allclose(P, P.T, atol=1e-12) and (np.linalg.eigvalsh(0.5 * (P + P.T)) > 0).all()
+    near, cnt = f.nearest(len(pr.scan))
+    assert (cnt == 5).all()
+    # the cached neighbours are the exact 5-NN of the LAST searched pose: re-query them on the device map
+    logs = f.pass_logs()
+    last_search = max(i for i, l in enumerate(logs) if l["searched"])
+    x_search = pr.x_prior if last_search == 0 else logs[last_search - 1]["x_after"]
+    idx = np.arange(0, len(pr.scan), 97)
+    q = np.zeros((len(idx), 4), dtype=np.float32)
+    tmp = np.zeros(3, dtype=np.float32)
+    for k, i in enumerate(idx):
+        bind.lib().oracle_transform_point(np.ascontiguousarray(x_search), np.ascontiguousarray(pr.scan[i, :3]), tmp)
+        q[k, :3] = tmp
+    port = bind.KdTree(pr.map_pts, "port")
+    pp, pd, pc = port.knn(q, 5)
+    assert np.array_equal(near[idx][:, :, :3], pp[:, :, :3])

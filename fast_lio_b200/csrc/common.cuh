@@ -51,14 +51,12 @@ __device__ __forceinline__ float sq_dist3(float ax, float ay, float az, float bx
 // calc_box_dist (ikd_Tree.cpp:1691-1709): squared distance from a point to an AABB
 __device__ __forceinline__ float box_dist3(float qx, float qy, float qz, float lx, float ly, float lz,
                                            float hx, float hy, float hz) {
-    float m = 0.0f;
-    if (qx < lx) { float d = __fsub_rn(qx, lx); m = __fadd_rn(m, __fmul_rn(d, d)); }
-    if (qx > hx) { float d = __fsub_rn(qx, hx); m = __fadd_rn(m, __fmul_rn(d, d)); }
-    if (qy < ly) { float d = __fsub_rn(qy, ly); m = __fadd_rn(m, __fmul_rn(d, d)); }
-    if (qy > hy) { float d = __fsub_rn(qy, hy); m = __fadd_rn(m, __fmul_rn(d, d)); }
-    if (qz < lz) { float d = __fsub_rn(qz, lz); m = __fadd_rn(m, __fmul_rn(d, d)); }
-    if (qz > hz) { float d = __fsub_rn(qz, hz); m = __fadd_rn(m, __fmul_rn(d, d)); }
-    return m;
+    // per axis at most one of (q < lo), (q > hi) holds, and (q - lo)^2 == (lo - q)^2 exactly, so
+    // max(lo - q, q - hi, 0)^2 summed x, y, z reproduces the reference's value bit for bit
+    const float dx = fmaxf(fmaxf(__fsub_rn(lx, qx), __fsub_rn(qx, hx)), 0.0f);
+    const float dy = fmaxf(fmaxf(__fsub_rn(ly, qy), __fsub_rn(qy, hy)), 0.0f);
+    const float dz = fmaxf(fmaxf(__fsub_rn(lz, qz), __fsub_rn(qz, hz)), 0.0f);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
 // ----------------------------------------------------------------------------- Morton keys

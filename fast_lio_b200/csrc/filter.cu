@@ -370,7 +370,8 @@ __device__ void apply_cols(double* mat, const double* J3, const double* J6, cons
 // of different warps so that the FP64 chains (and their instruction fetches) overlap.
 #define STAMP(i) do { if (threadIdx.x == 0) ctl->prof[i] = clock64(); } while (0)
 
-__device__ __noinline__ void solve_prepare(SolveShared& S, const FilterCtl* ctl, int solver) {
+template <int SOLVER>
+__device__ __noinline__ void solve_prepare(SolveShared& S, const FilterCtl* ctl) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     constexpr int n = NDOF;
     if (lane == 0) {
@@ -409,7 +410,7 @@ __device__ __noinline__ void solve_prepare(SolveShared& S, const FilterCtl* ctl,
     apply_cols(S.P, S.J[0], S.J[1], S.M2, 0);
     __syncthreads();
     S.prep_ok = 1;
-    if (solver == 0) {
+    if constexpr (SOLVER == 0) {
         // first half of esekfom.hpp:1782:  P_temp = (P/R)^{-1}  -> S.L  (independent of H)
         const double R = ctl->R;
 #pragma unroll 1
@@ -433,44 +434,12 @@ __device__ __noinline__ void solve_prepare(SolveShared& S, const FilterCtl* ctl,
     }
 }
 
-__device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const ScanView& sc, PassLog* logs, int solver) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+// small-m branch, esekfom.hpp:1715-1744 (T6):  K = P H^T (H P H^T / R + I)^{-1} / R ;  K_h = K h ;  K_x = K H.
+// Cold path (fewer than 23 effective points), kept out of line.
+__device__ __noinline__ bool solve_gain_small_m(SolveShared& S, const FilterCtl* ctl, const ScanView& sc, int extr, double R) {
+    const int tid = threadIdx.x, nt = blockDim.x;
     constexpr int n = NDOF;
-    STAMP(1);
-    if (tid < 144) { const int a = tid / 12, b = tid % 12; S.HTH[tid] = S.red[a <= b ? tri12(a, b) : tri12(b, a)]; }
-    if (tid < 12) S.Hth[tid] = S.red[78 + tid];
-    const int effct = (int)(S.red[90] + 0.5);
-    const int it = ctl->iter, max_iter = ctl->max_iter, n_pass = ctl->n_pass;
-    const int searched = ctl->converge;
-    const int t_in = ctl->t;
-    const int extr = ctl->extrinsic_est;
-    const double R = ctl->R;
-    PassLog* lg = (logs && n_pass < MAX_LOGS) ? &logs[n_pass] : nullptr;
-    // ------------------------------------------------------------------ invalid pass (laserMapping.cpp:708-713, esekfom.hpp:1638-1641)
-    if (effct < 1) {
-        if (tid == 0) {
-            if (lg) {
-                lg->searched = searched; lg->effct = 0; lg->res_sum = 0.0; lg->valid = 0;
-                lg->converged = searched; for (int i = 0; i < XLEN; i++) lg->x_after[i] = ctl->x[i];
-            }
-            ctl->n_pass = n_pass + 1;
-            ctl->iter = it + 1;
-            if (it + 1 >= max_iter) ctl->done = 1;
-        }
-        return;
-    }
-    __syncthreads();
-    if (lg) {
-        if (tid < 144) lg->HtH[tid] = S.HTH[tid];
-        if (tid < 12) lg->Hth[tid] = S.Hth[tid];
-        if (tid == 0) { lg->searched = searched; lg->effct = effct; lg->res_sum = S.red[91]; lg->valid = 1; }
-    }
-    bool ok = S.prep_ok != 0;
-    const int ne = extr ? 12 : 6;          // with extrinsic_est_en == false, columns 6..11 of h_x are zero
-    if (!ok) {
-        // fall through to the error exit below
-    } else if (effct < n) {
-        // -------------------------------------------------------------- small-m branch, esekfom.hpp:1715-1744 (T6)
+    bool ok = true;
         //   K = P H^T (H P H^T / R + I)^{-1} / R ;  K_h = K h ;  K_x = K H
         // the m (< 23) Jacobian rows are rebuilt, in point order, from what k_residual left per point
         if (tid == 0) {
@@ -532,7 +501,49 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
                 if (j < 12) S.Kx[i * 12 + j] = v; else S.Kh[i] = v;
             }
         }
-    } else if (solver == 0) {
+    return ok;
+}
+
+template <int SOLVER, bool EXTR>
+__device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const ScanView& sc, PassLog* logs) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int n = NDOF;
+    STAMP(1);
+    if (tid < 144) { const int a = tid / 12, b = tid % 12; S.HTH[tid] = S.red[a <= b ? tri12(a, b) : tri12(b, a)]; }
+    if (tid < 12) S.Hth[tid] = S.red[78 + tid];
+    const int effct = (int)(S.red[90] + 0.5);
+    const int it = ctl->iter, max_iter = ctl->max_iter, n_pass = ctl->n_pass;
+    const int searched = ctl->converge;
+    const int t_in = ctl->t;
+    constexpr int extr = EXTR ? 1 : 0;
+    const double R = ctl->R;
+    PassLog* lg = (logs && n_pass < MAX_LOGS) ? &logs[n_pass] : nullptr;
+    // ------------------------------------------------------------------ invalid pass (laserMapping.cpp:708-713, esekfom.hpp:1638-1641)
+    if (effct < 1) {
+        if (tid == 0) {
+            if (lg) {
+                lg->searched = searched; lg->effct = 0; lg->res_sum = 0.0; lg->valid = 0;
+                lg->converged = searched; for (int i = 0; i < XLEN; i++) lg->x_after[i] = ctl->x[i];
+            }
+            ctl->n_pass = n_pass + 1;
+            ctl->iter = it + 1;
+            if (it + 1 >= max_iter) ctl->done = 1;
+        }
+        return;
+    }
+    __syncthreads();
+    if (lg) {
+        if (tid < 144) lg->HtH[tid] = S.HTH[tid];
+        if (tid < 12) lg->Hth[tid] = S.Hth[tid];
+        if (tid == 0) { lg->searched = searched; lg->effct = effct; lg->res_sum = S.red[91]; lg->valid = 1; }
+    }
+    bool ok = S.prep_ok != 0;
+    constexpr int ne = EXTR ? 12 : 6;       // with extrinsic_est_en == false, columns 6..11 of h_x are zero
+    if (!ok) {
+        // fall through to the error exit below
+    } else if (effct < n) {
+        ok = solve_gain_small_m(S, ctl, sc, extr, R);
+    } else if constexpr (SOLVER == 0) {
         // -------------------------------------------------------------- information form exactly as the reference, esekfom.hpp:1782-1809
         //   P_temp = (P/R)^{-1} (S.L, from solve_prepare);  P_temp[0:12,0:12] += H^T H;  P_inv = P_temp^{-1}
 #pragma unroll 1
@@ -570,7 +581,7 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
         // -- algebraically identical to esekfom.hpp:1782-1809 without the two 23x23 inversions.
         // Rows/columns ne..11 of H^T H are zero when the extrinsic columns are (ne = 6): the system
         // is then block upper-triangular and only its leading ne x ne block needs eliminating.
-        const int ld = ne + ne + 1;                       // <= 25 columns: one lane each
+        constexpr int ld = ne + ne + 1;                   // <= 25 columns: one lane each
         const double Rinv = 1.0 / R;
         const int nwarps = nt >> 5;
 #pragma unroll 1
@@ -579,7 +590,7 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
                 double v;
                 if (lane < ne) {
                     v = 0.0;
-#pragma unroll 1
+#pragma unroll
                     for (int k = 0; k < ne; k++) v += S.HTH[r * 12 + k] * (S.P[k * n + lane] * Rinv);
                     v += (r == lane ? 1.0 : 0.0);
                 } else if (lane == ne) v = S.Hth[r];
@@ -588,7 +599,10 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
             }
         }
         __syncthreads();
-        if (warp == 0) { const bool w_ok = gj_warp(S.aug, ne, ld, ld, S.row_of, lane); if (lane == 0) S.m_rows = w_ok ? 1 : 0; }
+        if (warp == 0) {
+            const bool w_ok = gj_warp_reg<ne>(S.aug, ld, ld, S.row_of, lane);
+            if (lane == 0) S.m_rows = w_ok ? 1 : 0;
+        }
         __syncthreads();
         ok = S.m_rows != 0;
         if (ok) {
@@ -605,7 +619,7 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
                 if (lane < 13) {
                     double v = 0.0;
                     if (lane <= ne) {
-#pragma unroll 1
+#pragma unroll
                         for (int a = 0; a < ne; a++) v += (S.P[i * n + a] * Rinv) * S.T[a * 13 + lane];
                     }
                     if (lane == 0) S.Kh[i] = v; else S.Kx[i * 12 + (lane - 1)] = v;
@@ -622,7 +636,7 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
     // ------------------------------------------------------------------ esekfom.hpp:1815-1817
     if (tid < n) {
         double v = S.Kh[tid];
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 12; j++) v += S.Kx[tid * 12 + j] * S.dx_new[j];
         const double d = v - S.dx_new[tid];                   // K_h + (K_x - I) dx_new
         S.dxu[tid] = d;
@@ -693,7 +707,7 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
     for (int e = tid; e < n * n; e += nt) {                     // P_ = L_ - K_x[:, 0:12] P_[0:12, :]
         const int i = e / n, j = e % n;
         double v = 0.0;
-#pragma unroll 1
+#pragma unroll
         for (int a = 0; a < 12; a++) v += S.Kx[i * 12 + a] * S.P[a * n + j];
         ctl->P[e] = S.L[e] - v;
     }
@@ -711,9 +725,9 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
 //   mode 0: finishes the Kalman step of this pass on the spot (single GPU -- no extra launch),
 //   mode 1: publishes the 92 sums for the all-reduce across ranks (k_solve_only follows).
 // Waiting cannot deadlock: block 0 holds no resource another block needs in order to run.
-template <bool EXTR>
+template <bool EXTR, int SOLVER>
 __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterCtl* ctl, double* __restrict__ partials,
-                                                             double* red_g, int mode, PassLog* logs, int solver) {
+                                                             double* red_g, int mode, PassLog* logs) {
     __shared__ SolveShared S;
     if (ctl->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -748,7 +762,7 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
     }
     // ------------------------------------------------------------------ solver block
     STAMP(0);
-    if (mode == 0) solve_prepare(S, ctl, solver);
+    if (mode == 0) solve_prepare<SOLVER>(S, ctl);
     STAMP(8);
     if (threadIdx.x == 0) {
         while (atomicAdd(&ctl->ticket, 0) < nwork) __nanosleep(64);
@@ -777,18 +791,19 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
         __syncthreads();
     }
     if (mode == 1) return;
-    solve_finish(S, ctl, sc, logs, solver);
+    solve_finish<SOLVER, EXTR>(S, ctl, sc, logs);
 }
 
 // multi-GPU: the Kalman step from the all-reduced sums
+template <bool EXTR, int SOLVER>
 __global__ void __launch_bounds__(RESID_THREADS) k_solve_only(FilterCtl* ctl, const double* __restrict__ red_g, ScanView sc,
-                                                              PassLog* logs, int solver) {
+                                                              PassLog* logs) {
     __shared__ SolveShared S;
     if (ctl->done) return;
-    solve_prepare(S, ctl, solver);
+    solve_prepare<SOLVER>(S, ctl);
     if (threadIdx.x < NRED) S.red[threadIdx.x] = red_g[threadIdx.x];
     __syncthreads();
-    solve_finish(S, ctl, sc, logs, solver);
+    solve_finish<SOLVER, EXTR>(S, ctl, sc, logs);
 }
 #undef STAMP
 
@@ -950,7 +965,9 @@ int Filter::run_passes() {
             cudaStream_t st = stream();
             int rc = nccl_->AllReduce(red_.ptr, red_.ptr, NRED, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm_, st);
             if (rc != 0) { set_last_error("ncclAllReduce failed: %d", rc); return FL_ERR_NCCL; }
-            k_solve_only<<<1, RESID_THREADS, 0, st>>>(ctl_.as<FilterCtl>(), red_.as<double>(), scan_, logs_.as<PassLog>(), solver_);
+            FilterCtl* c = ctl_.as<FilterCtl>(); double* rg = red_.as<double>(); PassLog* lg = logs_.as<PassLog>();
+            if (extrinsic_est_) { if (solver_) k_solve_only<true, 1><<<1, RESID_THREADS, 0, st>>>(c, rg, scan_, lg); else k_solve_only<true, 0><<<1, RESID_THREADS, 0, st>>>(c, rg, scan_, lg); }
+            else { if (solver_) k_solve_only<false, 1><<<1, RESID_THREADS, 0, st>>>(c, rg, scan_, lg); else k_solve_only<false, 0><<<1, RESID_THREADS, 0, st>>>(c, rg, scan_, lg); }
             launches_++;
         }
     }
@@ -972,8 +989,15 @@ int Filter::launch_residual_only() {
     // worker blocks (one thread per point, grid-stride beyond max_resid_grid_ - 1 blocks) + the solver block 0
     resid_grid_ = std::min(max_resid_grid_ - 1, (nq + RESID_THREADS - 1) / RESID_THREADS) + 1;
     const int mode = nranks_ > 1 ? 1 : 0;
-    if (extrinsic_est_) k_residual<true><<<resid_grid_, RESID_THREADS, 0, stream()>>>(scan_, ctl_.as<FilterCtl>(), partials_.as<double>(), red_.as<double>(), mode, logs_.as<PassLog>(), solver_);
-    else k_residual<false><<<resid_grid_, RESID_THREADS, 0, stream()>>>(scan_, ctl_.as<FilterCtl>(), partials_.as<double>(), red_.as<double>(), mode, logs_.as<PassLog>(), solver_);
+    FilterCtl* c = ctl_.as<FilterCtl>(); double* pp = partials_.as<double>(); double* rg = red_.as<double>(); PassLog* lg = logs_.as<PassLog>();
+    cudaStream_t st = stream();
+    if (extrinsic_est_) {
+        if (solver_) k_residual<true, 1><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg);
+        else k_residual<true, 0><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg);
+    } else {
+        if (solver_) k_residual<false, 1><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg);
+        else k_residual<false, 0><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg);
+    }
     FL_CUDA(cudaGetLastError());
     return FL_OK;
 }

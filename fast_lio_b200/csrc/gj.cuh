@@ -70,4 +70,46 @@ __device__ bool gj_warp(double* a, int n, int nc, int ld, int* row_of, int lane)
     return true;
 }
 
+// Register-resident variant for N = 6 / 12: lane j keeps column j of [A | B] (nc <= 32 columns) in
+// registers, the pivot column is broadcast with shuffles; the rows of a step are unrolled, the
+// steps are not -- no shared-memory traffic, no dependent LDS chains, small code.
+template <int N>
+__device__ __forceinline__ bool gj_warp_reg(double* a, int nc, int ld, int* row_of, int lane) {
+    __syncwarp();
+    double c[N];
+#pragma unroll
+    for (int r = 0; r < N; r++) c[r] = lane < nc ? a[r * ld + lane] : 0.0;
+    unsigned used = 0;
+    bool ok = true;
+#pragma unroll 1                                   // one compact step body, re-executed N times (instruction-cache friendly)
+    for (int k = 0; k < N; k++) {
+        int p = 0; double best = -1.0;
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+            const double v = fabs(c[r]);
+            const bool cand = !((used >> r) & 1u) && v > best;
+            best = cand ? v : best; p = cand ? r : p;
+        }
+        p = __shfl_sync(FULL, p, k);
+        best = __shfl_sync(FULL, best, k);
+        if (!(best > 0.0)) ok = false;
+        double apj = 0.0;
+#pragma unroll
+        for (int r = 0; r < N; r++) apj = (r == p) ? c[r] : apj;
+        const double inv = 1.0 / __shfl_sync(FULL, apj, k);
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+            const double ck = __shfl_sync(FULL, c[r], k);
+            if (r != p && lane > k) c[r] -= (ck * inv) * apj;
+        }
+        used |= 1u << p;
+        if (lane == 0) row_of[k] = p;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int r = 0; r < N; r++) if (lane < nc) a[r * ld + lane] = c[r];
+    __syncwarp();
+    return ok;
+}
+
 }  // namespace fl

@@ -53,10 +53,12 @@ __device__ __forceinline__ unsigned flip_float(float f) {
     return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
 }
 // split leaf of a segment covering leaves [a, b), b - a >= 2
-__host__ __device__ __forceinline__ int split_leaf(int a, int b) {
+// pmax = leaves under one child of the root: above it the root's (up to 64) children are split
+// evenly instead of on powers of 32
+__host__ __device__ __forceinline__ int split_leaf(int a, int b, long long pmax) {
     const int span = b - a;
     long long p = 1;
-    while (p * FAN < span) p *= FAN;
+    while (p * FAN < span && p * FAN <= pmax) p *= FAN;
     const int nch = (int)((span + p - 1) / p);
     return a + (int)((nch / 2) * p);
 }
@@ -118,14 +120,14 @@ __global__ void k_kd_keys(const float4* __restrict__ src, const unsigned* __rest
     keys[r] = ((unsigned long long)(unsigned)s << 32) | flip_float(c);
     vals[r] = id;
 }
-__global__ void k_kd_split(const Segment* __restrict__ in, Segment* __restrict__ out, int nseg, int fill) {
+__global__ void k_kd_split(const Segment* __restrict__ in, Segment* __restrict__ out, int nseg, int fill, long long pmax) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseg) return;
     const Segment g = in[s];
     Segment l = g, r;
     r.p0 = r.p1 = g.p1; r.a = r.b = g.b;
     if (g.b - g.a >= 2) {
-        const int m = split_leaf(g.a, g.b);
+        const int m = split_leaf(g.a, g.b, pmax);
         long long cut = (long long)g.p0 + (long long)(m - g.a) * fill;
         if (cut > g.p1) cut = g.p1;
         l.p1 = (int)cut; l.b = m;
@@ -419,16 +421,22 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
         const float4 p = pts[i];
         int node = 0;
         for (int k = m.n_levels - 1; k >= 0; k--) {
-            const int e = node * FAN + lane;
+            const bool root = (k == m.n_levels - 1);
             unsigned key = 0xffffffffu;
-            if (e < m.count[k]) {
-                const float4 lo = m.ebox[k][2 * e], hi = m.ebox[k][2 * e + 1];
-                // empty entities have inverted boxes (distance +inf): they are the last resort
-                const float d = box_dist3(p.x, p.y, p.z, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-                key = (min(__float_as_uint(d), 0x7f800000u) & ~31u) | (unsigned)lane;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                if (half == 1 && !root) break;
+                const int c = lane + 32 * half;
+                const int e = root ? c : node * FAN + c;
+                if (e < m.count[k]) {
+                    const float4 lo = m.ebox[k][2 * e], hi = m.ebox[k][2 * e + 1];
+                    // empty entities have inverted boxes (distance +inf): they are the last resort
+                    const float d = box_dist3(p.x, p.y, p.z, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+                    key = min(key, (min(__float_as_uint(d), 0x7f800000u) & ~63u) | (unsigned)c);
+                }
             }
             const unsigned best = __reduce_min_sync(FULL, key);
-            node = node * FAN + (int)(best & 31u);
+            node = (root ? 0 : node * FAN) + (int)(best & 63u);
         }
         const int home = node;
         int leaf = home;
@@ -532,10 +540,9 @@ int Map::ensure_capacity(int n_points) {
         const int c = v_.count[k];
         FL_CHECK(ebox_[k].reserve(sizeof(float4) * 2 * (size_t)c));
         v_.ebox[k] = ebox_[k].as<float4>();
-        const int up = (c + FAN - 1) / FAN;
         k++;
-        v_.count[k] = up;
-        if (up == 1) break;
+        if (c <= ROOT_FAN) { v_.count[k] = 1; break; }          // the root owns up to 64 entities of level k-1
+        v_.count[k] = (c + FAN - 1) / FAN;
         if (k >= MAX_LEVELS) { set_last_error("too many tree levels"); return FL_ERR_CAPACITY; }
     }
     v_.n_levels = k;
@@ -551,10 +558,10 @@ int Map::refit() {
     return FL_OK;
 }
 
-static int kd_depth(int span) {
+static int kd_depth(int span, long long pmax) {
     if (span <= 1) return 0;
-    const int m = split_leaf(0, span);
-    return 1 + std::max(kd_depth(m), kd_depth(span - m));
+    const int m = split_leaf(0, span, pmax);
+    return 1 + std::max(kd_depth(m, pmax), kd_depth(span - m, pmax));
 }
 
 // d_src: n points (x, y, z, intensity) on the device, any order.
@@ -564,7 +571,9 @@ int Map::build_from_sorted(const float4* d_src, int n) {
     k_clear_leaves<<<blocks_for((long long)v_.leaf_cap * LEAF, 256), 256, 0, stream_>>>(v_);
     if (n > 0) {
         const int L = v_.n_main;
-        const int depth = kd_depth(L);
+        long long pmax = 1;
+        for (int k = 1; k < v_.n_levels; k++) pmax *= FAN;            // leaves under one child of the root
+        const int depth = kd_depth(L, pmax);
         const size_t max_seg = (size_t)1 << depth;
         FL_CHECK(keys_in_.reserve(sizeof(unsigned long long) * (size_t)n));
         FL_CHECK(keys_out_.reserve(sizeof(unsigned long long) * (size_t)n));
@@ -593,7 +602,7 @@ int Map::build_from_sorted(const float4* d_src, int n) {
             tmp = cub_tmp_.bytes;
             FL_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp_.ptr, tmp, keys_in_.as<unsigned long long>(), keys_out_.as<unsigned long long>(),
                                                     idx_tmp, idx, n, 0, end_bit, stream_));
-            k_kd_split<<<blocks_for(nseg, 256, 1 << 30), 256, 0, stream_>>>(segtab_[cur].as<Segment>(), segtab_[cur ^ 1].as<Segment>(), nseg, fill_);
+            k_kd_split<<<blocks_for(nseg, 256, 1 << 30), 256, 0, stream_>>>(segtab_[cur].as<Segment>(), segtab_[cur ^ 1].as<Segment>(), nseg, fill_, pmax);
             k_kd_assign<<<nb, 256, 0, stream_>>>(keys_out_.as<unsigned long long>(), n, segtab_[cur ^ 1].as<Segment>(), segid);
             cur ^= 1;
         }

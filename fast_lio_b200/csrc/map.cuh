@@ -106,17 +106,45 @@ __device__ __forceinline__ void knn_node(const MapView& m, int node, float qx, f
     }
 }
 
+// The root owns up to 64 entities (two per lane), which saves the two nearly empty top levels a
+// strict 32-ary hierarchy would have (1 M points: 41 667 leaves -> 1 303 -> 41 -> root).
+constexpr int ROOT_FAN = 64;
+
+template <int L>
+__device__ __forceinline__ void knn_root(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
+    const int cnt = m.count[L - 1];
+    float d0 = INFINITY, d1 = INFINITY;
+    if (lane < cnt) {
+        const float4 lo = __ldg(&m.ebox[L - 1][2 * lane]), hi = __ldg(&m.ebox[L - 1][2 * lane + 1]);
+        d0 = box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+    }
+    if (lane + 32 < cnt) {
+        const float4 lo = __ldg(&m.ebox[L - 1][2 * (lane + 32)]), hi = __ldg(&m.ebox[L - 1][2 * (lane + 32) + 1]);
+        d1 = box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+    }
+#pragma unroll 1
+    while (true) {
+        const unsigned k0 = (d0 < kb.w) ? ((__float_as_uint(d0) & ~63u) | (unsigned)lane) : 0xffffffffu;
+        const unsigned k1 = (d1 < kb.w) ? ((__float_as_uint(d1) & ~63u) | (unsigned)(lane + 32)) : 0xffffffffu;
+        const unsigned best = __reduce_min_sync(FULL, min(k0, k1));
+        if (best == 0xffffffffu) break;
+        const int c = best & 63;
+        if (lane == (c & 31)) { if (c < 32) d0 = INFINITY; else d1 = INFINITY; }
+        if constexpr (L == 1) knn_leaf(m, c, qx, qy, qz, kb, lane);
+        else knn_node<L - 1>(m, c, qx, qy, qz, kb, lane);
+    }
+}
+
 // Exact k-nearest-neighbour search for one query by one warp.
 __device__ __forceinline__ void knn_query(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
     kb.init();
     switch (m.n_levels) {
-        case 1: knn_node<1>(m, 0, qx, qy, qz, kb, lane); break;
-        case 2: knn_node<2>(m, 0, qx, qy, qz, kb, lane); break;
-        case 3: knn_node<3>(m, 0, qx, qy, qz, kb, lane); break;
-        case 4: knn_node<4>(m, 0, qx, qy, qz, kb, lane); break;
-        case 5: knn_node<5>(m, 0, qx, qy, qz, kb, lane); break;
-        case 6: knn_node<6>(m, 0, qx, qy, qz, kb, lane); break;
-        default: knn_node<7>(m, 0, qx, qy, qz, kb, lane); break;
+        case 1: knn_root<1>(m, qx, qy, qz, kb, lane); break;
+        case 2: knn_root<2>(m, qx, qy, qz, kb, lane); break;
+        case 3: knn_root<3>(m, qx, qy, qz, kb, lane); break;
+        case 4: knn_root<4>(m, qx, qy, qz, kb, lane); break;
+        case 5: knn_root<5>(m, qx, qy, qz, kb, lane); break;
+        default: knn_root<6>(m, qx, qy, qz, kb, lane); break;
     }
 }
 
@@ -153,16 +181,35 @@ __device__ __forceinline__ void box_node(const MapView& m, int node, const float
         else box_node<L - 1, F>(m, node * FAN + c, bmin, bmax, f, lane);
     }
 }
+template <int L, class F>
+__device__ __forceinline__ void box_root(const MapView& m, const float* bmin, const float* bmax, F& f, int lane) {
+    const int cnt = m.count[L - 1];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int e = lane + 32 * half;
+        bool hit = false;
+        if (e < cnt) {
+            const float4 lo = __ldg(&m.ebox[L - 1][2 * e]), hi = __ldg(&m.ebox[L - 1][2 * e + 1]);
+            hit = box_overlaps(lo, hi, bmin, bmax);
+        }
+        unsigned mask = __ballot_sync(FULL, hit);
+        while (mask) {
+            const int c = __ffs(mask) - 1 + 32 * half;
+            mask &= mask - 1;
+            if constexpr (L == 1) f.leaf(c);
+            else box_node<L - 1, F>(m, c, bmin, bmax, f, lane);
+        }
+    }
+}
 template <class F>
 __device__ __forceinline__ void box_query(const MapView& m, const float* bmin, const float* bmax, F& f, int lane) {
     switch (m.n_levels) {
-        case 1: box_node<1, F>(m, 0, bmin, bmax, f, lane); break;
-        case 2: box_node<2, F>(m, 0, bmin, bmax, f, lane); break;
-        case 3: box_node<3, F>(m, 0, bmin, bmax, f, lane); break;
-        case 4: box_node<4, F>(m, 0, bmin, bmax, f, lane); break;
-        case 5: box_node<5, F>(m, 0, bmin, bmax, f, lane); break;
-        case 6: box_node<6, F>(m, 0, bmin, bmax, f, lane); break;
-        default: box_node<7, F>(m, 0, bmin, bmax, f, lane); break;
+        case 1: box_root<1, F>(m, bmin, bmax, f, lane); break;
+        case 2: box_root<2, F>(m, bmin, bmax, f, lane); break;
+        case 3: box_root<3, F>(m, bmin, bmax, f, lane); break;
+        case 4: box_root<4, F>(m, bmin, bmax, f, lane); break;
+        case 5: box_root<5, F>(m, bmin, bmax, f, lane); break;
+        default: box_root<6, F>(m, bmin, bmax, f, lane); break;
     }
 }
 

@@ -17,13 +17,33 @@ __global__ void k_block(const double* in, double* out, int n, int nrhs, int* okf
     if (threadIdx.x == 0) *okflag = ok;
     for (int e = threadIdx.x; e < n * nrhs; e += blockDim.x) { int k = e / nrhs, j = e % nrhs; out[e] = a[row_of[k] * ld + n + j] / a[row_of[k] * ld + k]; }
 }
+__global__ void k_time(const double* in, int n, int nrhs, long long* t) {
+    __shared__ double a[12 * 32];
+    __shared__ int row_of[32];
+    const int nc = n + nrhs, ld = nc;
+    for (int rep = 0; rep < 3; rep++) {
+        for (int e = threadIdx.x; e < n * nc; e += blockDim.x) a[e] = in[e];
+        __syncthreads();
+        long long t0 = clock64();
+        if (threadIdx.x < 32) { if (n == 6) gj_warp_reg<6>(a, nc, ld, row_of, threadIdx.x); else gj_warp_reg<12>(a, nc, ld, row_of, threadIdx.x); }
+        __syncthreads();
+        long long t1 = clock64();
+        for (int e = threadIdx.x; e < n * nc; e += blockDim.x) a[e] = in[e];
+        __syncthreads();
+        long long t2 = clock64();
+        if (threadIdx.x < 32) gj_warp(a, n, nc, ld, row_of, threadIdx.x);
+        __syncthreads();
+        long long t3 = clock64();
+        if (threadIdx.x == 0) { t[rep * 2] = t1 - t0; t[rep * 2 + 1] = t3 - t2; }
+    }
+}
 __global__ void k_warp(const double* in, double* out, int n, int nrhs, int* okflag) {
     __shared__ double a[12 * 32];
     __shared__ int row_of[32];
     const int nc = n + nrhs, ld = nc;
     for (int e = threadIdx.x; e < n * nc; e += blockDim.x) a[e] = in[e];
     __syncthreads();
-    if (threadIdx.x < 32) { bool ok = gj_warp(a, n, nc, ld, row_of, threadIdx.x); if (threadIdx.x == 0) *okflag = ok; }
+    if (threadIdx.x < 32) { bool ok = n == 6 ? gj_warp_reg<6>(a, nc, ld, row_of, threadIdx.x) : (n == 12 ? gj_warp_reg<12>(a, nc, ld, row_of, threadIdx.x) : gj_warp(a, n, nc, ld, row_of, threadIdx.x)); if (threadIdx.x == 0) *okflag = ok; }
     __syncthreads();
     for (int e = threadIdx.x; e < n * nrhs; e += blockDim.x) { int k = e / nrhs, j = e % nrhs; out[e] = a[row_of[k] * ld + n + j] / a[row_of[k] * ld + k]; }
 }
@@ -58,6 +78,7 @@ int main() {
             double md = 0, mr = 0; for (size_t i = 0; i < got.size(); i++) { md = fmax(md, fabs(got[i] - ref[i])); mr = fmax(mr, fabs(ref[i])); }
             printf("n=%d nrhs=%d nt=%d %s: err=%s maxdiff=%.3e (max |x|=%.3e)\n", n, nrhs, nt, which ? "warp" : "block", cudaGetErrorString(e), md, mr);
         }
+        if (n <= 12) { long long* dt; cudaMalloc(&dt, 64); k_time<<<1, 256>>>(din, n, nrhs, dt); long long ht[6]; cudaMemcpy(ht, dt, 48, cudaMemcpyDeviceToHost); printf("  cycles reg/smem: rep0 %lld / %lld  rep1 %lld / %lld  rep2 %lld / %lld\n", ht[0], ht[1], ht[2], ht[3], ht[4], ht[5]); }
     }
     return 0;
 }

@@ -36,7 +36,7 @@ _lib = None
 
 # every symbol include/fastlio_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "fl_last_error", "fl_device_count", "fl_version",
+    "fl_last_error", "fl_device_count", "fl_version", "fl_host_register", "fl_host_unregister", "fl_filter_debug_prof",
     "fl_map_create", "fl_map_destroy", "fl_map_set_downsample", "fl_map_build", "fl_map_size", "fl_map_validnum",
     "fl_map_knn", "fl_map_add_points", "fl_map_delete_boxes", "fl_map_flatten", "fl_map_tree_range",
     "fl_map_rebuild", "fl_map_stats",
@@ -62,6 +62,8 @@ def load():
                            "there is no CPU fallback")
     L = C.CDLL(_build.LIB)
     L.fl_last_error.restype = C.c_char_p
+    L.fl_host_register.argtypes = [C.c_void_p, C.c_ulonglong]
+    L.fl_host_unregister.argtypes = [C.c_void_p]
     L.fl_map_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_float]
     L.fl_map_destroy.argtypes = [C.c_void_p]
     L.fl_map_set_downsample.argtypes = [C.c_void_p, C.c_float]
@@ -278,6 +280,15 @@ class Esekf:
 
     def set_shard(self, q_begin: int, q_end: int):
         _check(self._L.fl_filter_set_shard(self.h, q_begin, q_end))
+
+
+def host_register(arr: np.ndarray):
+    """Page-lock a numpy array that will be passed repeatedly (the reference's scan buffer)."""
+    _check(load().fl_host_register(arr.ctypes.data, arr.nbytes))
+
+
+def host_unregister(arr: np.ndarray):
+    _check(load().fl_host_unregister(arr.ctypes.data))
 
 
 def comm_unique_id() -> bytes:

@@ -33,6 +33,17 @@ int fl_device_count(void) {
     return n;
 }
 
+int fl_host_register(const void* ptr, unsigned long long bytes) {
+    if (!ptr || !bytes) return FL_ERR_ARG;
+    FL_CUDA(cudaHostRegister(const_cast<void*>(ptr), (size_t)bytes, cudaHostRegisterDefault));
+    return FL_OK;
+}
+int fl_host_unregister(const void* ptr) {
+    if (!ptr) return FL_ERR_ARG;
+    FL_CUDA(cudaHostUnregister(const_cast<void*>(ptr)));
+    return FL_OK;
+}
+
 // ------------------------------------------------------------------------------------ map
 int fl_map_create(fl_map_t** out, int device, float downsample_size) {
     if (!out) { fl::set_last_error("fl_map_create: null out"); return FL_ERR_ARG; }

@@ -45,6 +45,10 @@ typedef struct fl_pass_log {
 } fl_pass_log_t;
 
 const char* fl_last_error(void);
+/* Page-lock a caller-owned, long-lived host buffer (e.g. the scan buffer reused every scan) so that
+ * fl_filter_update / fl_map_add_points copy from it by DMA; unregister before freeing it. */
+int fl_host_register(const void* ptr, unsigned long long bytes);
+int fl_host_unregister(const void* ptr);
 int fl_device_count(void);
 int fl_version(void);
 
@@ -113,6 +117,8 @@ int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_to
 /* device time of `reps` launches of the dominant kernel alone (k_measure in search mode) */
 int fl_filter_time_search_pass(fl_filter_t* f, int reps, int flush_l2, float* ms_total);
 int fl_filter_gpu_launches(fl_filter_t* f);
+/* clock64() stamps of the last on-device Kalman step (tuning aid; layout in scripts/profile_once.py) */
+int fl_filter_debug_prof(fl_filter_t* f, long long* out16);
 
 /* ------------------------------------------------------------------ multi-GPU (no reference counterpart)
  * scan points are sharded across ranks, the map is replicated, the 92 normal-equation doubles

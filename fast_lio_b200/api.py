@@ -41,7 +41,7 @@ SYMBOLS = [
     "fl_map_knn", "fl_map_add_points", "fl_map_delete_boxes", "fl_map_flatten", "fl_map_tree_range",
     "fl_map_rebuild", "fl_map_stats",
     "fl_filter_create", "fl_filter_destroy", "fl_filter_set_params", "fl_filter_set_solver", "fl_filter_update",
-    "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
+    "fl_filter_map_incremental", "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
     "fl_filter_upload_state", "fl_filter_run", "fl_filter_download_state", "fl_filter_sync",
     "fl_filter_time_resident", "fl_filter_time_search_pass", "fl_filter_gpu_launches",
     "fl_comm_unique_id", "fl_filter_comm_init", "fl_filter_set_shard",
@@ -82,6 +82,7 @@ def load():
     L.fl_filter_set_params.argtypes = [C.c_void_p, C.c_int, _f64p, C.c_int]
     L.fl_filter_set_solver.argtypes = [C.c_void_p, C.c_int]
     L.fl_filter_update.argtypes = [C.c_void_p, _f32p, C.c_int, _f64p, _f64p, C.c_double, C.POINTER(C.c_double)]
+    L.fl_filter_map_incremental.argtypes = [C.c_void_p, C.c_double, C.c_int, _i32p]
     L.fl_filter_get_nearest.argtypes = [C.c_void_p, _f32p, _i32p, C.c_int]
     L.fl_filter_get_selected.argtypes = [C.c_void_p, _u8p, C.c_int]
     L.fl_filter_get_pass_logs.argtypes = [C.c_void_p, C.POINTER(PassLog), C.c_int]
@@ -220,6 +221,12 @@ class Esekf:
         st = C.c_double(0.0)
         _check(self._L.fl_filter_update(self.h, scan4, len(scan4), x, Pm, R, C.byref(st)))
         return x, Pm, st.value
+
+    def map_incremental(self, filter_size_map_min: float = 0.5, flg_EKF_inited: bool = True):
+        """laserMapping.cpp:427-474 on the device; returns (|PointToAdd|, |PointNoNeedDownsample|, Add_Points return)."""
+        out = np.zeros(3, dtype=np.int32)
+        _check(self._L.fl_filter_map_incremental(self.h, filter_size_map_min, int(flg_EKF_inited), out))
+        return int(out[0]), int(out[1]), int(out[2])
 
     def nearest(self, nq: int):
         pts = np.zeros((nq, 5, 4), dtype=np.float32)

@@ -138,6 +138,13 @@ int fl_filter_update(fl_filter_t* f, const float* body, int nq, double* x26, dou
     FILTER_GUARD(f);
     return f->impl->update(body, nq, x26, P, R, solve_time_s);
 }
+int fl_filter_map_incremental(fl_filter_t* f, double fsm, int ekf_inited, int* out3) {
+    FILTER_GUARD(f);
+    int a = 0, b = 0, c = 0;
+    int rc = f->impl->map_incremental(fsm, ekf_inited, &a, &b, &c);
+    if (out3) { out3[0] = a; out3[1] = b; out3[2] = c; }
+    return rc;
+}
 int fl_filter_get_nearest(fl_filter_t* f, float* out_pts, int* out_cnt, int nq) { FILTER_GUARD(f); return f->impl->get_nearest(out_pts, out_cnt, nq); }
 int fl_filter_get_selected(fl_filter_t* f, unsigned char* out, int nq) { FILTER_GUARD(f); if (!out) return FL_ERR_ARG; return f->impl->get_selected(out, nq); }
 int fl_filter_get_pass_logs(fl_filter_t* f, fl_pass_log_t* out, int cap) {

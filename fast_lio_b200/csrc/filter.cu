@@ -14,6 +14,8 @@
 
 #include <algorithm>
 
+#include <cub/device/device_select.cuh>
+
 #include "filter.h"
 #include "gj.cuh"
 
@@ -807,6 +809,43 @@ __global__ void __launch_bounds__(RESID_THREADS) k_solve_only(FilterCtl* ctl, co
 }
 #undef STAMP
 
+// ============================================================================= map_incremental
+// laserMapping.cpp:427-474: which scan points enter the map, and how.  One thread per point.
+__global__ void k_map_incremental(ScanView sc, const FilterCtl* __restrict__ ctl, double fsm, int ekf_inited,
+                                  float4* __restrict__ world, unsigned char* __restrict__ flag_add, unsigned char* __restrict__ flag_no) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= sc.Q) return;
+    const PoseS s = load_pose(ctl->x);                                   // state_point after the update (:961)
+    const float4 pb = __ldg(&sc.body[q]);
+    float w[3];
+    body_to_world(s, pb, w[0], w[1], w[2]);                              // pointBodyToWorld :177-186
+    world[q] = make_float4(w[0], w[1], w[2], pb.w);
+    int cls = 0;                                                         // 0: PointToAdd, 1: PointNoNeedDownsample, 2: neither
+    const int cnt = sc.nearest_cnt[q];
+    if (cnt > 0 && ekf_inited) {                                         // :438
+        float mid[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) mid[a] = (float)(floor((double)w[a] / fsm) * fsm + 0.5 * fsm);     // :444-446
+        const float dist = sq_dist3(w[0], w[1], w[2], mid[0], mid[1], mid[2]);                           // :447 calc_dist (common_lib.h:219-222)
+        const float4 n0 = sc.nearest[(size_t)q * KNN_K];
+        if ((double)fabsf(__fsub_rn(n0.x, mid[0])) > 0.5 * fsm && (double)fabsf(__fsub_rn(n0.y, mid[1])) > 0.5 * fsm &&
+            (double)fabsf(__fsub_rn(n0.z, mid[2])) > 0.5 * fsm) {        // :448
+            cls = 1;
+        } else {
+            bool need_add = true;
+            if (cnt >= KNN_K) {                                          // :454
+                for (int j = 0; j < KNN_K; j++) {
+                    const float4 nj = sc.nearest[(size_t)q * KNN_K + j];
+                    if (sq_dist3(nj.x, nj.y, nj.z, mid[0], mid[1], mid[2]) < dist) { need_add = false; break; }      // :455
+                }
+            }
+            cls = need_add ? 0 : 2;
+        }
+    }
+    flag_add[q] = cls == 0;
+    flag_no[q] = cls == 1;
+}
+
 // ============================================================================= NCCL (lazy)
 struct NcclUniqueId { char internal[128]; };
 struct NcclApi {
@@ -855,6 +894,7 @@ Filter::~Filter() {
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     body_.release(); nearest_.release(); nearest_cnt_.release(); selected_.release(); normvec_.release();
     partials_.release(); red_.release(); ctl_.release(); ctl0_.release(); logs_.release();
+    mi_world_.release(); mi_flag_add_.release(); mi_flag_no_.release(); mi_list_add_.release(); mi_list_no_.release(); mi_tmp_.release(); mi_counts_.release();
     if (h_ctl_) cudaFreeHost(h_ctl_);
 }
 
@@ -1039,6 +1079,47 @@ int Filter::update(const float* body_xyzi, int nq, double* x26, double* P, doubl
         *solve_time_s += ms * 1e-3;                       // the reference accumulates into solve_time (esekfom.hpp:1926)
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
+    return FL_OK;
+}
+
+int Filter::map_incremental(double fsm, int ekf_inited, int* n_to_add, int* n_no_downsample, int* added) {
+    if (n_to_add) *n_to_add = 0;
+    if (n_no_downsample) *n_no_downsample = 0;
+    if (added) *added = 0;
+    const int nq = scan_.Q;
+    if (nq <= 0) return FL_OK;
+    if (!(fsm > 0.0)) { set_last_error("map_incremental: filter_size_map_min must be > 0"); return FL_ERR_ARG; }
+    FL_CUDA(cudaSetDevice(map_->device()));
+    cudaStream_t st = stream();
+    FL_CHECK(mi_world_.reserve(sizeof(float4) * (size_t)nq));
+    FL_CHECK(mi_flag_add_.reserve((size_t)nq));
+    FL_CHECK(mi_flag_no_.reserve((size_t)nq));
+    FL_CHECK(mi_list_add_.reserve(sizeof(float4) * (size_t)nq));
+    FL_CHECK(mi_list_no_.reserve(sizeof(float4) * (size_t)nq));
+    FL_CHECK(mi_counts_.reserve(sizeof(int) * 2));
+    k_map_incremental<<<(nq + 255) / 256, 256, 0, st>>>(scan_, ctl_.as<FilterCtl>(), fsm, ekf_inited, mi_world_.as<float4>(),
+                                                       mi_flag_add_.as<unsigned char>(), mi_flag_no_.as<unsigned char>());
+    FL_CUDA(cudaGetLastError());
+    // order-preserving compaction: Add_Points is sequential in the batch order (ikd_Tree.cpp:487)
+    size_t tmp = 0;
+    FL_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp, mi_world_.as<float4>(), mi_flag_add_.as<unsigned char>(), mi_list_add_.as<float4>(),
+                                       mi_counts_.as<int>(), nq, st));
+    FL_CHECK(mi_tmp_.reserve(tmp));
+    tmp = mi_tmp_.bytes;
+    FL_CUDA(cub::DeviceSelect::Flagged(mi_tmp_.ptr, tmp, mi_world_.as<float4>(), mi_flag_add_.as<unsigned char>(), mi_list_add_.as<float4>(),
+                                       mi_counts_.as<int>(), nq, st));
+    tmp = mi_tmp_.bytes;
+    FL_CUDA(cub::DeviceSelect::Flagged(mi_tmp_.ptr, tmp, mi_world_.as<float4>(), mi_flag_no_.as<unsigned char>(), mi_list_no_.as<float4>(),
+                                       mi_counts_.as<int>() + 1, nq, st));
+    int counts[2] = {0, 0};
+    FL_CUDA(cudaMemcpyAsync(counts, mi_counts_.ptr, sizeof(counts), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(cudaStreamSynchronize(st));
+    if (n_to_add) *n_to_add = counts[0];
+    if (n_no_downsample) *n_no_downsample = counts[1];
+    int a = 0, b = 0;
+    FL_CHECK(map_->add_points_device(mi_list_add_.as<float4>(), counts[0], true, &a));      // :470
+    FL_CHECK(map_->add_points_device(mi_list_no_.as<float4>(), counts[1], false, &b));      // :471
+    if (added) *added = a;
     return FL_OK;
 }
 

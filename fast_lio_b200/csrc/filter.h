@@ -73,6 +73,9 @@ public:
     int download_state(double* x26, double* P, int* n_pass);
     int sync();
 
+    // map_incremental (laserMapping.cpp:427-474) on the device: classify every scan point with the final
+    // state and its cached neighbours, then Add_Points(PointToAdd, true) + Add_Points(PointNoNeedDownsample, false)
+    int map_incremental(double filter_size_map_min, int ekf_inited, int* n_to_add, int* n_no_downsample, int* added);
     int get_nearest(float* out_pts, int* out_cnt, int nq);
     int get_selected(unsigned char* out, int nq);
     int get_pass_logs(PassLog* out, int cap, int* n);
@@ -97,6 +100,7 @@ private:
     int solver_ = 0;
     ScanView scan_;
     DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, partials_, red_, ctl_, ctl0_, logs_;
+    DeviceBuffer mi_world_, mi_flag_add_, mi_flag_no_, mi_list_add_, mi_list_no_, mi_tmp_, mi_counts_;
     FilterCtl* h_ctl_ = nullptr;       // pinned staging
     int sms_ = 0, search_grid_max_ = 0, max_resid_grid_ = 0, resid_grid_ = 1;
     int launches_ = 0;

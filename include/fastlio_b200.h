@@ -99,6 +99,10 @@ int fl_filter_set_solver(fl_filter_t* f, int mode);
  * x26 / P: in = kf.get_x()/get_P() before the update, out = after.  solve_time_s (may be NULL)
  * is incremented by the device time of the update, like the reference's out-parameter. */
 int fl_filter_update(fl_filter_t* f, const float* body_xyzi, int nq, double* x26, double* P, double R, double* solve_time_s);
+/* map_incremental() (laserMapping.cpp:427-474) without leaving the device: classifies the bound scan with the
+ * updated state and the cached neighbours, then performs the two Add_Points calls (:470-471).
+ * out3 (may be NULL): [0] |PointToAdd| [1] |PointNoNeedDownsample| [2] return value of Add_Points(PointToAdd, true) */
+int fl_filter_map_incremental(fl_filter_t* f, double filter_size_map_min, int flg_EKF_inited, int* out3);
 /* Nearest_Points after the update (laserMapping.cpp:102, read by map_incremental :438-460) */
 int fl_filter_get_nearest(fl_filter_t* f, float* out_pts, int* out_cnt, int nq);
 /* point_selected_surf after the update (laserMapping.cpp:76) */

@@ -83,3 +83,36 @@ def sort_rows(a):
         return a
     order = np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))
     return a[order]
+
+
+def map_incremental(scan4, x26, nearest, nearest_cnt, fsm=0.5, ekf_inited=True):
+    """Restatement of map_incremental's decision logic (reference src/laserMapping.cpp:427-474).
+    Returns (PointToAdd, PointNoNeedDownsample) as float32 arrays of world points, in scan order."""
+    from oracle import bind
+    L = bind.lib()
+    to_add, no_need = [], []
+    w = np.zeros(3, dtype=np.float32)
+    x26 = np.ascontiguousarray(x26, dtype=np.float64)
+    fsm = float(fsm)
+    for i in range(len(scan4)):
+        L.oracle_transform_point(x26, np.ascontiguousarray(scan4[i, :3]), w)                  # pointBodyToWorld :177-186
+        pw = np.array([w[0], w[1], w[2], scan4[i, 3]], dtype=np.float32)
+        cnt = int(nearest_cnt[i])
+        if cnt > 0 and ekf_inited:                                                                # :438
+            mid = np.array([F(np.floor(float(w[a]) / fsm) * fsm + 0.5 * fsm) for a in range(3)], dtype=np.float32)   # :444-446
+            dist = VoxelMapModel._dist(pw, mid)                                                   # :447
+            n0 = nearest[i, 0]
+            if all(float(abs(F(n0[a] - mid[a]))) > 0.5 * fsm for a in range(3)):                  # :448
+                no_need.append(pw)
+                continue
+            need_add = True
+            if cnt >= 5:
+                for j in range(5):                                                                # :452-459
+                    if VoxelMapModel._dist(nearest[i, j], mid) < dist:
+                        need_add = False
+                        break
+            if need_add:
+                to_add.append(pw)
+        else:
+            to_add.append(pw)
+    return (np.array(to_add, dtype=np.float32).reshape(-1, 4), np.array(no_need, dtype=np.float32).reshape(-1, 4))

@@ -44,7 +44,7 @@ SYMBOLS = [
     "fl_filter_map_incremental", "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
     "fl_filter_upload_state", "fl_filter_run", "fl_filter_download_state", "fl_filter_sync",
     "fl_filter_time_resident", "fl_filter_time_search_pass", "fl_filter_gpu_launches",
-    "fl_comm_unique_id", "fl_filter_comm_init", "fl_filter_set_shard",
+    "fl_comm_unique_id", "fl_filter_comm_init", "fl_filter_set_shard", "fl_filter_p2p_handle", "fl_filter_p2p_connect",
 ]
 
 
@@ -97,6 +97,8 @@ def load():
     L.fl_comm_unique_id.argtypes = [C.c_char_p]
     L.fl_filter_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
     L.fl_filter_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.fl_filter_p2p_handle.argtypes = [C.c_void_p, C.c_char_p]
+    L.fl_filter_p2p_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
     _lib = L
     return L
 
@@ -284,6 +286,14 @@ class Esekf:
 
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
         _check(self._L.fl_filter_comm_init(self.h, nranks, rank, unique_id))
+
+    def p2p_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self._L.fl_filter_p2p_handle(self.h, buf))
+        return buf.raw
+
+    def p2p_connect(self, nranks: int, rank: int, handles: bytes):
+        _check(self._L.fl_filter_p2p_connect(self.h, nranks, rank, handles))
 
     def set_shard(self, q_begin: int, q_end: int):
         _check(self._L.fl_filter_set_shard(self.h, q_begin, q_end))

@@ -241,6 +241,8 @@ int fl_filter_comm_init(fl_filter_t* f, int nranks, int rank, const void* id128)
     if (nranks > 1 && !id128) return FL_ERR_ARG;
     return f->impl->comm_init(nranks, rank, id128);
 }
+int fl_filter_p2p_handle(fl_filter_t* f, void* out64) { FILTER_GUARD(f); if (!out64) return FL_ERR_ARG; return f->impl->p2p_local_handle(out64); }
+int fl_filter_p2p_connect(fl_filter_t* f, int nranks, int rank, const void* handles) { FILTER_GUARD(f); return f->impl->p2p_connect(nranks, rank, handles); }
 int fl_filter_set_shard(fl_filter_t* f, int q_begin, int q_end) { FILTER_GUARD(f); return f->impl->set_shard(q_begin, q_end); }
 
 }  // extern "C"

@@ -729,7 +729,7 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
 // Waiting cannot deadlock: block 0 holds no resource another block needs in order to run.
 template <bool EXTR, int SOLVER>
 __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterCtl* ctl, double* __restrict__ partials,
-                                                             double* red_g, int mode, PassLog* logs) {
+                                                             double* red_g, int mode, PassLog* logs, P2PState* p2p) {
     __shared__ SolveShared S;
     if (ctl->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
     }
     // ------------------------------------------------------------------ solver block
     STAMP(0);
-    if (mode == 0) solve_prepare<SOLVER>(S, ctl);
+    if (mode != 1) solve_prepare<SOLVER>(S, ctl);
     STAMP(8);
     if (threadIdx.x == 0) {
         while (atomicAdd(&ctl->ticket, 0) < nwork) __nanosleep(64);
@@ -793,6 +793,40 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
         __syncthreads();
     }
     if (mode == 1) return;
+    if (mode == 2) {
+        // ---- all-reduce over peer memory, fused: publish my 92 sums into every rank's mailbox, raise my
+        // epoch flag there, wait for everybody's flag here, add the rows in rank order (bit-identical on all ranks)
+        const int nr = p2p->nranks, me = p2p->rank;
+        const unsigned long long epoch = p2p->epoch + 1;
+        const int par = (int)(epoch & 1ull);
+        for (int r = warp; r < nr; r += NW) {
+            double* dst = p2p->peer_mail[r] + ((size_t)par * nr + me) * PSTRIDE;
+            for (int o = lane; o < PSTRIDE; o += 32) dst[o] = S.red[o];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < nr) {
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p2p->peer_flag[threadIdx.x] + me), "l"(epoch) : "memory");
+            const unsigned long long* mine = p2p->peer_flag[me] + threadIdx.x;
+            unsigned long long seen = 0;
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+                if (seen >= epoch) break;
+                __nanosleep(32);
+            } while (clock64() - t0 < 4000000000ll);              // ~2 s: a dead peer must not hang the GPU
+            if (seen < epoch) ctl->error = 2;
+        }
+        __syncthreads();
+        if (threadIdx.x < PSTRIDE) {
+            const double* mail = p2p->peer_mail[me] + (size_t)par * nr * PSTRIDE;
+            double v = 0.0;
+            for (int r = 0; r < nr; r++) v += __ldcg(&mail[(size_t)r * PSTRIDE + threadIdx.x]);
+            S.red[threadIdx.x] = v;
+        }
+        if (threadIdx.x == 0) p2p->epoch = epoch;
+        __syncthreads();
+    }
     solve_finish<SOLVER, EXTR>(S, ctl, sc, logs);
 }
 
@@ -892,6 +926,8 @@ Filter::Filter(Map* map, int max_points) : map_(map), max_points_(max_points) {
 Filter::~Filter() {
     cudaSetDevice(map_->device());
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
+    for (int r = 0; r < P2P_MAX_RANKS; r++) if (peer_ptr_[r]) cudaIpcCloseMemHandle(peer_ptr_[r]);
+    mailbox_.release(); p2p_.release();
     body_.release(); nearest_.release(); nearest_cnt_.release(); selected_.release(); normvec_.release();
     partials_.release(); red_.release(); ctl_.release(); ctl0_.release(); logs_.release();
     mi_world_.release(); mi_flag_add_.release(); mi_flag_no_.release(); mi_list_add_.release(); mi_list_no_.release(); mi_tmp_.release(); mi_counts_.release();
@@ -1001,7 +1037,7 @@ int Filter::run_passes() {
         FL_CHECK(launch_search_only());
         FL_CHECK(launch_residual_only());
         launches_ += 2;
-        if (nranks_ > 1) {
+        if (nranks_ > 1 && !p2p_on_) {
             cudaStream_t st = stream();
             int rc = nccl_->AllReduce(red_.ptr, red_.ptr, NRED, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm_, st);
             if (rc != 0) { set_last_error("ncclAllReduce failed: %d", rc); return FL_ERR_NCCL; }
@@ -1028,15 +1064,16 @@ int Filter::launch_residual_only() {
     const int nq = scan_.q_end - scan_.q_begin;
     // worker blocks (one thread per point, grid-stride beyond max_resid_grid_ - 1 blocks) + the solver block 0
     resid_grid_ = std::min(max_resid_grid_ - 1, (nq + RESID_THREADS - 1) / RESID_THREADS) + 1;
-    const int mode = nranks_ > 1 ? 1 : 0;
+    const int mode = nranks_ > 1 ? (p2p_on_ ? 2 : 1) : 0;
+    P2PState* p2p = p2p_.as<P2PState>();
     FilterCtl* c = ctl_.as<FilterCtl>(); double* pp = partials_.as<double>(); double* rg = red_.as<double>(); PassLog* lg = logs_.as<PassLog>();
     cudaStream_t st = stream();
     if (extrinsic_est_) {
-        if (solver_) k_residual<true, 1><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg);
-        else k_residual<true, 0><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg);
+        if (solver_) k_residual<true, 1><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg, p2p);
+        else k_residual<true, 0><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg, p2p);
     } else {
-        if (solver_) k_residual<false, 1><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg);
-        else k_residual<false, 0><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg);
+        if (solver_) k_residual<false, 1><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg, p2p);
+        else k_residual<false, 0><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg, p2p);
     }
     FL_CUDA(cudaGetLastError());
     return FL_OK;
@@ -1148,6 +1185,46 @@ int Filter::get_pass_logs(PassLog* out, int cap, int* n) {
         FL_CUDA(cudaStreamSynchronize(stream()));
     }
     if (n) *n = np;
+    return FL_OK;
+}
+
+int Filter::p2p_local_handle(void* out64) {
+    FL_CUDA(cudaSetDevice(map_->device()));
+    const size_t bytes = sizeof(double) * 2 * P2P_MAX_RANKS * PSTRIDE + sizeof(unsigned long long) * P2P_MAX_RANKS;
+    if (!mailbox_.ptr) {
+        FL_CHECK(mailbox_.reserve(bytes));
+        FL_CUDA(cudaMemset(mailbox_.ptr, 0, mailbox_.bytes));
+    }
+    cudaIpcMemHandle_t h;
+    FL_CUDA(cudaIpcGetMemHandle(&h, mailbox_.ptr));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(out64, &h, 64);
+    return FL_OK;
+}
+
+int Filter::p2p_connect(int nranks, int rank, const void* handles64) {
+    if (nranks < 1 || nranks > P2P_MAX_RANKS || rank < 0 || rank >= nranks || !handles64) { set_last_error("p2p_connect: bad arguments"); return FL_ERR_ARG; }
+    if (!mailbox_.ptr) { set_last_error("p2p_connect: call p2p_local_handle first"); return FL_ERR_STATE; }
+    FL_CUDA(cudaSetDevice(map_->device()));
+    P2PState st;
+    memset(&st, 0, sizeof(st));
+    st.nranks = nranks; st.rank = rank; st.epoch = 0;
+    for (int r = 0; r < nranks; r++) {
+        void* base = mailbox_.ptr;
+        if (r != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)handles64 + 64 * r, 64);
+            FL_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            peer_ptr_[r] = base;
+        }
+        st.peer_mail[r] = (double*)base;
+        st.peer_flag[r] = (unsigned long long*)((char*)base + sizeof(double) * 2 * P2P_MAX_RANKS * PSTRIDE);
+    }
+    // NOTE the mailbox stride uses P2P_MAX_RANKS rows per parity only for the allocation size; rows are indexed [par * nranks + r]
+    FL_CHECK(p2p_.reserve(sizeof(P2PState)));
+    FL_CUDA(cudaMemcpy(p2p_.ptr, &st, sizeof(st), cudaMemcpyHostToDevice));
+    nranks_ = nranks; rank_ = rank;
+    p2p_on_ = nranks > 1;
     return FL_OK;
 }
 

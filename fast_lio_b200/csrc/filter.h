@@ -51,6 +51,16 @@ struct ScanView {
 
 struct NcclApi;
 
+// Peer-memory exchange of the per-pass sums (fused into k_residual's solver block): every rank owns a
+// mailbox [2 epochs parity][nranks][96] doubles + nranks epoch flags; peers store into it over NVLink.
+constexpr int P2P_MAX_RANKS = 8;
+struct P2PState {
+    double* peer_mail[P2P_MAX_RANKS];                 // mailbox of rank r (mapped through CUDA IPC)
+    unsigned long long* peer_flag[P2P_MAX_RANKS];     // its flag array
+    unsigned long long epoch;                         // passes exchanged so far (identical on all ranks)
+    int nranks, rank;
+};
+
 class Filter {
 public:
     Filter(Map* map, int max_points);
@@ -82,6 +92,9 @@ public:
     // multi-GPU: scan points sharded across ranks, map replicated, one all-reduce per pass
     int comm_init(int nranks, int rank, const void* nccl_unique_id_128);
     int set_shard(int q_begin, int q_end);             // default: the whole scan
+    // fused all-reduce over NVLink peer memory instead of NCCL (one kernel per pass)
+    int p2p_local_handle(void* out64);
+    int p2p_connect(int nranks, int rank, const void* handles64);
 
     int gpu_launches() const { return launches_; }
     const float4* nearest_device() const { return scan_.nearest; }
@@ -109,6 +122,9 @@ private:
     NcclApi* nccl_ = nullptr;
     void* comm_ = nullptr;
     int nranks_ = 1, rank_ = 0;
+    DeviceBuffer mailbox_, p2p_;
+    void* peer_ptr_[P2P_MAX_RANKS] = {nullptr};
+    bool p2p_on_ = false;
 };
 
 }  // namespace fl

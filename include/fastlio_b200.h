@@ -130,6 +130,11 @@ int fl_filter_debug_prof(fl_filter_t* f, long long* out16);
 int fl_comm_unique_id(void* out128);
 int fl_filter_comm_init(fl_filter_t* f, int nranks, int rank, const void* unique_id128);
 int fl_filter_set_shard(fl_filter_t* f, int q_begin, int q_end);
+/* Same exchange without NCCL, fused into the residual kernel: each rank exports its mailbox as a 64-byte CUDA-IPC
+ * handle (fl_filter_p2p_handle), the application all-gathers the handles, fl_filter_p2p_connect maps the peers.
+ * Per pass every rank stores its 92 sums straight into its peers' mailboxes over NVLink and spins on epoch flags. */
+int fl_filter_p2p_handle(fl_filter_t* f, void* out64);
+int fl_filter_p2p_connect(fl_filter_t* f, int nranks, int rank, const void* handles /* nranks x 64 bytes */);
 
 #ifdef __cplusplus
 }

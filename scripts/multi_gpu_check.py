@@ -15,15 +15,21 @@ f1 = api.Esekf(t, max_points=len(pr.scan), max_iter=pr.cfg.max_iter)
 x1, P1, _ = f1.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
 # sharded
 f = api.Esekf(t, max_points=len(pr.scan), max_iter=pr.cfg.max_iter)
-uid = [api.comm_unique_id() if rank == 0 else None]
-dist.broadcast_object_list(uid, src=0)
-f.comm_init(world, rank, uid[0])
+comm = sys.argv[2] if len(sys.argv) > 2 else "p2p"
+if comm == "p2p":
+    handles = [None] * world
+    dist.all_gather_object(handles, f.p2p_handle())
+    f.p2p_connect(world, rank, b"".join(handles))
+else:
+    uid = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    f.comm_init(world, rank, uid[0])
 lo, hi = api.shard_range(len(pr.scan), world, rank)
 f.set_shard(lo, hi)
 x, P, _ = f.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
 dx = float(np.abs(x - x1).max()); dP = float(np.abs(P - P1).max())
 xs = torch.tensor(x, device="cuda"); ref = xs.clone(); dist.broadcast(ref, src=0)
 same = bool((xs == ref).all().item())
-print(f"rank {rank}/{world}: shard [{lo},{hi}) |x - x_1gpu|={dx:.3e} |P - P_1gpu|={dP:.3e} identical_to_rank0={same} passes={len(f.pass_logs())}", flush=True)
+print(f"[{comm}] rank {rank}/{world}: shard [{lo},{hi}) |x - x_1gpu|={dx:.3e} |P - P_1gpu|={dP:.3e} identical_to_rank0={same} passes={len(f.pass_logs())}", flush=True)
 assert dx < 1e-9 and dP < 1e-9 and same
 dist.barrier(); dist.destroy_process_group()

@@ -193,7 +193,7 @@ class Esekf:
     """esekf::update_iterated_dyn_share_modified with the fused device measurement model."""
 
     def __init__(self, tree: KdTree, max_points: int = 100000, max_iter: int = 4, limit: float = 0.001,
-                 extrinsic_est_en: bool = False, solver: int = 0):
+                 extrinsic_est_en: bool = False, solver: int = 1):
         self._L = load()
         self.tree = tree
         h = C.c_void_p()

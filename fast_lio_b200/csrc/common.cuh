@@ -59,29 +59,6 @@ __device__ __forceinline__ float box_dist3(float qx, float qy, float qz, float l
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// ----------------------------------------------------------------------------- Morton keys
-// 21 bits per axis on a fixed 1/32 m lattice centred on the origin (+-32.7 km); values
-// outside are clamped -- keys only order points for locality, correctness never depends
-// on them (AABBs are computed from the actual coordinates).
-__host__ __device__ __forceinline__ uint64_t spread21(uint32_t v) {
-    uint64_t x = v & 0x1fffffu;
-    x = (x | x << 32) & 0x1f00000000ffffULL;
-    x = (x | x << 16) & 0x1f0000ff0000ffULL;
-    x = (x | x << 8) & 0x100f00f00f00f00fULL;
-    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
-    x = (x | x << 2) & 0x1249249249249249ULL;
-    return x;
-}
-__host__ __device__ __forceinline__ uint32_t quant21(float v) {
-    float s = floorf(v * 32.0f) + 1048576.0f;
-    s = s < 0.0f ? 0.0f : (s > 2097151.0f ? 2097151.0f : s);
-    return (uint32_t)s;
-}
-__host__ __device__ __forceinline__ uint64_t morton_key(float x, float y, float z) {
-    if (!(x == x) || !(y == y) || !(z == z)) return 0;
-    return spread21(quant21(x)) | (spread21(quant21(y)) << 1) | (spread21(quant21(z)) << 2);
-}
-
 // ----------------------------------------------------------------------------- float atomics
 __device__ __forceinline__ void atomic_min_float(float* addr, float v) {
     // works for any finite / infinite floats (no NaN)

@@ -67,7 +67,7 @@ public:
     ~Filter();
     int init();
     int set_params(int max_iter, const double* limit23, int extrinsic_est_en);
-    void set_solver(int mode) { solver_ = mode; }       // 0: reference-mirroring two 23x23 inverses; 1: 12x12 Woodbury form
+    void set_solver(int mode) { solver_ = mode; }       // 1 (default): one ne x ne solve; 0: the reference's two 23x23 inversions, literally
 
     // whole update with host buffers (scan H2D, state H2D, passes, state D2H)
     int update(const float* body_xyzi, int nq, double* x26, double* P, double R, double* solve_time_s);
@@ -110,7 +110,7 @@ private:
     int max_iter_ = 4;
     double limit_[NDOF];
     int extrinsic_est_ = 0;
-    int solver_ = 0;
+    int solver_ = 1;
     ScanView scan_;
     DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, partials_, red_, ctl_, ctl0_, logs_;
     DeviceBuffer mi_world_, mi_flag_add_, mi_flag_no_, mi_list_add_, mi_list_no_, mi_tmp_, mi_counts_;

@@ -91,8 +91,9 @@ int fl_filter_create(fl_filter_t** out, fl_map_t* map, int max_points);
 int fl_filter_destroy(fl_filter_t* f);
 /* maximum_iter, limit[23], extrinsic_est_en (laserMapping.cpp:739,789) */
 int fl_filter_set_params(fl_filter_t* f, int max_iter, const double* limit23, int extrinsic_est_en);
-/* 0: information form with two 23x23 inversions as written at esekfom.hpp:1782-1809 (default);
- * 1: the same gain through one 12x12 solve */
+/* 1 (default): the gain of esekfom.hpp:1782-1809 through one 6x6 (12x12 with extrinsic estimation) solve,
+ *    algebraically identical;
+ * 0: the information form with two 23x23 inversions exactly as written in the reference (validation) */
 int fl_filter_set_solver(fl_filter_t* f, int mode);
 /* esekf::update_iterated_dyn_share_modified(R, solve_time) with feats_down_body bound
  *                                                                   esekfom.hpp:1619-1931, laserMapping.cpp:638-754, :960

@@ -114,20 +114,35 @@ def algorithmic_bytes_search(n_map: int, k: int = 5) -> int:
 
 
 def cpu_update_loop(pr, n_scans: int, nthreads: int, warm: int = 1):
-    """Times the CPU reference path: returns (seconds per scan list, kind)."""
+    """Times the CPU reference path.  The reference's OpenMP loop (laserMapping.cpp:646-650) does not
+    scale to every core count (allocation inside KD_TREE::Nearest_Search), so the thread count is
+    calibrated first -- one scan each at nproc, nproc/2, ... >= 4 -- and the fastest is used: the baseline is
+    the reference's best, not a strawman.  Returns (seconds per scan list, kind, threads used)."""
     from oracle import bind
     tree = bind.KdTree(pr.map_pts, "auto")
     kind = "reference" if tree.backend == "reference" else "port"
-    times = []
-    for i in range(warm + n_scans):
+
+    def one(nt):
         t0 = time.perf_counter()
         bind.update_iterated(tree, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit,
-                             pr.extrinsic_est_en, nthreads=nthreads)
-        dt = time.perf_counter() - t0
+                             pr.extrinsic_est_en, nthreads=nt)
+        return time.perf_counter() - t0
+
+    one(nthreads)                                   # warm the tree / page cache
+    cands, nt = [], nthreads
+    while nt >= 4:
+        cands.append(nt)
+        nt //= 2
+    if not cands:
+        cands = [max(1, nthreads)]
+    best = min(cands, key=lambda c: min(one(c), one(c)))
+    times = []
+    for i in range(warm + n_scans):
+        dt = one(best)
         if i >= warm:
             times.append(dt)
     tree.close()
-    return times, kind
+    return times, kind, best
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -137,7 +152,7 @@ def run_reference(args, rank: int):
     from fast_lio_b200 import synth
     pr = synth.make_problem(args.workload)
     cores = os.cpu_count() or 1
-    times, kind = cpu_update_loop(pr, args.steps, cores, warm=max(1, args.warmup))
+    times, kind, cores = cpu_update_loop(pr, args.steps, cores, warm=max(1, args.warmup))
     total = float(np.sum(times))
     val = len(times) / total
     line = {
@@ -146,7 +161,7 @@ def run_reference(args, rank: int):
         "vs_baseline": None, "dtype": "f32 geometry / f64 filter", "data": "synthetic",
         "config": {"workload": args.workload, "n_map": pr.cfg.n_map, "n_scan": pr.cfg.n_scan, "max_iteration": pr.cfg.max_iter},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{len(times)} full scan updates of the same workload, OpenMP over scan points"},
+                         "sample": f"{len(times)} full scan updates of the same workload, OpenMP over scan points, thread count calibrated (best of nproc, nproc/2, ...)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -248,9 +263,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n_cpu = max(3, min(40, args.cpu_scans))
-            times, kind = cpu_update_loop(pr, n_cpu, cores, warm=1)
+            times, kind, cores = cpu_update_loop(pr, n_cpu, cores, warm=1)
             cpu = {"value": len(times) / float(np.sum(times)), "unit": UNIT, "cores": cores, "kind": kind,
-                   "sample": f"{len(times)} full scan updates of the same workload (median {1e3 * float(np.median(times)):.1f} ms/scan)"}
+                   "sample": f"{len(times)} full scan updates of the same workload (median {1e3 * float(np.median(times)):.1f} ms/scan), thread count calibrated"}
         line = {
             "metric": METRIC, "value": args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

@@ -189,18 +189,27 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         comm = args.comm
         if comm == "p2p":
-            try:        # fused all-reduce over NVLink peer memory (CUDA IPC mailboxes), no NCCL on the data path
+            # fused all-reduce over NVLink peer memory (CUDA IPC mailboxes), no NCCL on the data path;
+            # the choice is collective: if any rank cannot map its peers, every rank uses NCCL
+            ok = 1
+            try:
                 handles = [None] * world
                 dist.all_gather_object(handles, filt.p2p_handle())
                 filt.p2p_connect(world, rank, b"".join(handles))
             except api.FastLioError as e:
-                if rank == 0:
-                    print(f"bench.py: peer-memory exchange unavailable ({e}); falling back to NCCL", file=sys.stderr)
+                print(f"bench.py[rank {rank}]: peer-memory exchange unavailable ({e})", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
                 comm = "nccl"
+                filt = api.Esekf(tree, max_points=Q, max_iter=pr.cfg.max_iter, limit=pr.limit,
+                                 extrinsic_est_en=bool(pr.extrinsic_est_en), solver=args.solver)
         if comm == "nccl":
             uid = [api.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             filt.comm_init(world, rank, uid[0])
+        args.comm = comm
         lo, hi = api.shard_range(Q, world, rank)
         filt.set_shard(lo, hi)
 

@@ -232,33 +232,67 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Fold the rows held by the 32 lanes into the lane-distributed accumulators: output o of the
-// NRED-vector lives in lane (o & 31), register acc[o >> 5].
+// NRED-vector lives in lane (o & 31), register acc[o >> 5].  The 32 rows are staged in the warp's
+// slice of shared memory and every lane accumulates its own outputs over the 32 rows (one LDS pair +
+// one FP64 multiply-add per row), instead of one 5-step shuffle butterfly per output.
+template <bool EXTR> struct RowStage { static constexpr int NC = EXTR ? 12 : 6; static constexpr int RS = NC + 2; };   // h[NC], z, pad
+
 template <bool EXTR>
-__device__ __forceinline__ void warp_accumulate(bool contrib, const double* h, double z, float absres, double (&acc)[3], int lane) {
-    constexpr int NC = EXTR ? 12 : 6;
+__device__ __forceinline__ void warp_accumulate(bool contrib, const double* h, double z, float absres, double (&acc)[3],
+                                                int lane, double* stage /* this warp's 32 x RS doubles */) {
+    constexpr int NC = RowStage<EXTR>::NC, RS = RowStage<EXTR>::RS;
+    constexpr int NPAIR = NC * (NC + 1) / 2;
     const unsigned any = __ballot_sync(FULL, contrib);
     if (!any) return;
 #pragma unroll
-    for (int a = 0; a < NC; a++) {
+    for (int a = 0; a < NC; a++) stage[lane * RS + a] = contrib ? h[a] : 0.0;
+    stage[lane * RS + NC] = contrib ? z : 0.0;
+    __syncwarp();
 #pragma unroll
-        for (int b = a; b < NC; b++) {
-            const int o = a * 12 - (a * (a - 1)) / 2 + (b - a);
-            const double v = warp_sum(contrib ? h[a] * h[b] : 0.0);
-            if (lane == (o & 31)) acc[o >> 5] += v;
+    for (int j = 0; j < 3; j++) {
+        const int t = lane + 32 * j;                      // t-th output of this pass: pairs (a<=b) row-major, then H^T h
+        if (t < NPAIR + NC) {
+            int a, b, o;
+            if (t < NPAIR) {
+                a = 0; int rem = t;
+                while (rem >= NC - a) { rem -= NC - a; a++; }
+                b = a + rem;
+                o = a * 12 - (a * (a - 1)) / 2 + (b - a);  // position in the 12-wide upper triangle
+            } else { a = t - NPAIR; b = NC; o = 78 + a; }
+            double v = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < 32; i++) v += stage[i * RS + a] * stage[i * RS + b];
+            // hand the sum to the lane/register that owns output o
+            // (t and o coincide lane-wise only when NC == 12; otherwise route through shared memory)
+            stage[32 * RS + t] = v;
+            (void)o;
         }
     }
+    __syncwarp();
 #pragma unroll
-    for (int a = 0; a < NC; a++) {
-        const int o = 78 + a;
-        const double v = warp_sum(contrib ? h[a] * z : 0.0);
-        if (lane == (o & 31)) acc[o >> 5] += v;
+    for (int j = 0; j < 3; j++) {
+        const int o = lane + 32 * j;                      // output owned by (lane, j)
+        if (o < 90) {
+            int t = -1;
+            if (o < 78) {
+                // invert tri12: find (a, b) of the 12-wide triangle
+                int a = 0, rem = o;
+                while (rem >= 12 - a) { rem -= 12 - a; a++; }
+                const int b = a + rem;
+                if (b < NC) t = a * NC - (a * (a - 1)) / 2 + (b - a);
+            } else if (o - 78 < NC) t = NPAIR + (o - 78);
+            if (t >= 0) acc[j] += stage[32 * RS + t];
+        }
     }
     {
         const double v = (double)__popc(any);
         if (lane == (90 & 31)) acc[90 >> 5] += v;
-        const double r = warp_sum(contrib ? (double)absres : 0.0);
+        double r = contrib ? (double)absres : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
         if (lane == (91 & 31)) acc[91 >> 5] += r;
     }
+    __syncwarp();
 }
 
 // k_search -- the kNN half of h_share_model (laserMapping.cpp:667-672).  One warp per scan
@@ -307,6 +341,8 @@ struct SolveShared {
     double red[PSTRIDE];
     double HTH[144];
     double Hth[12];
+    double wred[8 * PSTRIDE];     // per-warp partial sums (worker blocks: block partial; solver block: cross-block reduction)
+    // ---- from here to stage_end: reused by the worker blocks as row-staging area (see k_residual)
     double P[NDOF * NDOF];        // P_propagated after the manifold congruence (esekfom.hpp:1657-1699)
     double L[NDOF * NDOF];        // scratch, then L_ of the final covariance step
     double aug[NDOF * 2 * NDOF];  // augmented system for Gauss-Jordan
@@ -319,7 +355,8 @@ struct SolveShared {
     double rows[22 * 13];         // small-m branch: [h_x row (12) | h]
     double PHt[NDOF * 22];        // small-m branch
     double T[22 * 13];            // S^{-1} [h_x | h]  /  (I + M A11)^{-1} [H^T h | H^T H]
-    double wred[8 * PSTRIDE];     // per-warp partial sums of the cross-block reduction
+    double stage_pad[760];        // tops the staging area up to 8 warps x (32 x 14 + 96) doubles
+    double stage_end[1];
     int row_of[32], m_rows, finish, over, prep_ok;
     int row_idx[22];
 };
@@ -739,15 +776,19 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
         const int wb = (int)blockIdx.x - 1;
         const PoseS s = load_pose(ctl->x);
         double acc[3] = {0.0, 0.0, 0.0};
+        // worker blocks do not use the solver's matrices: their storage stages the warps' rows
+        constexpr int STAGE = 32 * RowStage<EXTR>::RS + 96;
+        static_assert(offsetof(SolveShared, stage_end) - offsetof(SolveShared, P) >= sizeof(double) * NW * STAGE, "staging area too small");
+        double* stage = S.P + warp * STAGE;
         const int q0 = sc.q_begin, q1 = sc.q_end;
         for (int base = q0 + wb * RESID_THREADS + warp * 32; base < q1; base += nwork * RESID_THREADS) {
             const int q = base + lane;
             double h[12]; double z = 0.0; float ar = 0.f;
             bool contrib = false;
             if (q < q1) contrib = measure_point<EXTR>(sc, q, s, h, z, ar);
-            warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane);
+            warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane, stage);
         }
-        double (*wacc)[PSTRIDE] = reinterpret_cast<double (*)[PSTRIDE]>(S.aug);     // NW x 96 doubles of scratch
+        double (*wacc)[PSTRIDE] = reinterpret_cast<double (*)[PSTRIDE]>(S.wred);     // NW x 96 doubles
 #pragma unroll
         for (int j = 0; j < 3; j++) wacc[warp][lane + 32 * j] = acc[j];
         __syncthreads();

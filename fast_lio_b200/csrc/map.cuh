@@ -45,7 +45,8 @@ struct KBest {
     float d;
     int idx;
     float w;
-    __device__ __forceinline__ void init() { d = INFINITY; idx = -1; w = INFINITY; }
+    int n;          // entries filled so far (warp-uniform)
+    __device__ __forceinline__ void init() { d = INFINITY; idx = -1; w = INFINITY; n = 0; }
     // nd, nidx warp-uniform, nd < w
     __device__ __forceinline__ void insert(float nd, int nidx, int lane) {
         const float up_d = __shfl_up_sync(FULL, d, 1);
@@ -67,6 +68,23 @@ __device__ __forceinline__ void knn_leaf(const MapView& m, int leaf, float qx, f
         const float4 p = __ldg(&m.pts[leaf * LEAF + lane]);
         const int nxt = __ldg(&m.next[leaf]);
         float d = slot_valid(p) ? sq_dist3(qx, qy, qz, p.x, p.y, p.z) : INFINITY;
+        if (kb.n == 0) {
+            // empty list (the first leaf of a query): the r-th smallest goes straight to lane r -- no merge
+            unsigned best = 0xffffffffu;
+#pragma unroll 1
+            for (int r = 0; r < KNN_K; r++) {
+                const unsigned key = (d < INFINITY) ? __float_as_uint(d) : 0xffffffffu;
+                best = __reduce_min_sync(FULL, key);
+                if (best == 0xffffffffu) break;
+                const int src = __ffs(__ballot_sync(FULL, key == best)) - 1;
+                if (lane == r) { kb.d = __uint_as_float(best); kb.idx = leaf * LEAF + src; }
+                if (lane == src) d = INFINITY;
+                kb.n = r + 1;
+            }
+            if (kb.n == KNN_K) kb.w = __uint_as_float(best);
+            leaf = nxt;
+            continue;
+        }
 #pragma unroll 1
         for (int it = 0; it < KNN_K; it++) {
             const unsigned key = (d < kb.w) ? __float_as_uint(d) : 0xffffffffu;   // d >= 0: bits order like floats

@@ -269,7 +269,7 @@ def make_map(n_map: int, seed: int = 1):
     return np.ascontiguousarray(pts), scene
 
 
-def make_scan(scene: Scene, n_scan: int, x_true: np.ndarray, seed: int = 2, noise_sigma: float = 0.02):
+def make_scan(scene: Scene, n_scan: int, x_true: np.ndarray, seed: int = 2, noise_sigma: float = 0.02, order: str = "voxelgrid"):
     """n_scan x 4 float32 body-frame points (x, y, z, intensity) of surfaces within range of
     the true sensor pose, one per VOXEL cell (the scan is voxel-filtered upstream,
     laserMapping.cpp:904-907), with `noise_sigma` range noise along the surface normal."""
@@ -304,7 +304,17 @@ def make_scan(scene: Scene, n_scan: int, x_true: np.ndarray, seed: int = 2, nois
     scan = np.empty((n, 4), dtype=np.float32)
     scan[:, :3] = p_b.astype(np.float32)
     scan[:, 3] = rng.uniform(1.0, 100.0, n).astype(np.float32)
-    scan = scan[rng.permutation(n)]
+    if order == "random":
+        scan = scan[rng.permutation(n)]
+    else:
+        # the update's input is the output of pcl::VoxelGrid (laserMapping.cpp:904-907), which emits one
+        # centroid per occupied leaf sorted by leaf index  ix + iy*nx + iz*nx*ny  (body frame): reproduce
+        # that ordering (x fastest, then y, then z)
+        cell = np.floor(scan[:, :3].astype(np.float64) / VOXEL).astype(np.int64)
+        cell -= cell.min(axis=0)
+        nx, ny = int(cell[:, 0].max()) + 1, int(cell[:, 1].max()) + 1
+        key = cell[:, 0] + cell[:, 1] * nx + cell[:, 2] * nx * ny
+        scan = scan[np.argsort(key, kind="stable")]
     return np.ascontiguousarray(scan)
 
 

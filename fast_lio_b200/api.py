@@ -40,7 +40,7 @@ SYMBOLS = [
     "fl_map_create", "fl_map_destroy", "fl_map_set_downsample", "fl_map_build", "fl_map_size", "fl_map_validnum",
     "fl_map_knn", "fl_map_add_points", "fl_map_delete_boxes", "fl_map_flatten", "fl_map_tree_range",
     "fl_map_rebuild", "fl_map_stats",
-    "fl_filter_create", "fl_filter_destroy", "fl_filter_set_params", "fl_filter_set_solver", "fl_filter_update",
+    "fl_filter_create", "fl_filter_destroy", "fl_filter_set_params", "fl_filter_set_solver", "fl_filter_set_search", "fl_filter_update",
     "fl_filter_map_incremental", "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
     "fl_filter_upload_state", "fl_filter_run", "fl_filter_download_state", "fl_filter_sync",
     "fl_filter_time_resident", "fl_filter_time_search_pass", "fl_filter_gpu_launches",
@@ -81,6 +81,7 @@ def load():
     L.fl_filter_destroy.argtypes = [C.c_void_p]
     L.fl_filter_set_params.argtypes = [C.c_void_p, C.c_int, _f64p, C.c_int]
     L.fl_filter_set_solver.argtypes = [C.c_void_p, C.c_int]
+    L.fl_filter_set_search.argtypes = [C.c_void_p, C.c_int]
     L.fl_filter_update.argtypes = [C.c_void_p, _f32p, C.c_int, _f64p, _f64p, C.c_double, C.POINTER(C.c_double)]
     L.fl_filter_map_incremental.argtypes = [C.c_void_p, C.c_double, C.c_int, _i32p]
     L.fl_filter_get_nearest.argtypes = [C.c_void_p, _f32p, _i32p, C.c_int]
@@ -193,7 +194,7 @@ class Esekf:
     """esekf::update_iterated_dyn_share_modified with the fused device measurement model."""
 
     def __init__(self, tree: KdTree, max_points: int = 100000, max_iter: int = 4, limit: float = 0.001,
-                 extrinsic_est_en: bool = False, solver: int = 1):
+                 extrinsic_est_en: bool = False, solver: int = 1, search: int = 0):
         self._L = load()
         self.tree = tree
         h = C.c_void_p()
@@ -203,6 +204,7 @@ class Esekf:
         lim = np.full(23, limit, dtype=np.float64)
         _check(self._L.fl_filter_set_params(self.h, max_iter, lim, int(extrinsic_est_en)))
         _check(self._L.fl_filter_set_solver(self.h, solver))
+        _check(self._L.fl_filter_set_search(self.h, search))
 
     def close(self):
         if getattr(self, "h", None):

@@ -67,6 +67,7 @@ public:
     ~Filter();
     int init();
     int set_params(int max_iter, const double* limit23, int extrinsic_est_en);
+    void set_search_mode(int mode) { search_mode_ = mode; }
     void set_solver(int mode) { solver_ = mode; }       // 1 (default): one ne x ne solve; 0: the reference's two 23x23 inversions, literally
 
     // whole update with host buffers (scan H2D, state H2D, passes, state D2H)
@@ -74,7 +75,7 @@ public:
     // pieces, for device-resident benchmarking / pipelines
     int upload_scan(const float* body_xyzi, int nq);
     int set_scan_device(const float4* d_body, int nq);
-    int upload_state(const double* x26, const double* P, double R);
+    int upload_state(const double* x26, const double* P, double R, bool snapshot = true);
     int restore_state();                               // device-side copy of the last uploaded state -> control block
     int run_passes();                                  // enqueue every pass on the stream (no sync)
     int launch_measure_only();
@@ -111,10 +112,12 @@ private:
     double limit_[NDOF];
     int extrinsic_est_ = 0;
     int solver_ = 1;
+    int search_mode_ = 0;              // 0: one warp per query (k_search, default); 1: one thread per query (k_search_t, measured 2.8x slower)
     ScanView scan_;
     DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, partials_, red_, ctl_, ctl0_, logs_;
     DeviceBuffer mi_world_, mi_flag_add_, mi_flag_no_, mi_list_add_, mi_list_no_, mi_tmp_, mi_counts_;
     FilterCtl* h_ctl_ = nullptr;       // pinned staging
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int sms_ = 0, search_grid_max_ = 0, max_resid_grid_ = 0, resid_grid_ = 1;
     int launches_ = 0;
     bool shard_set_ = false;

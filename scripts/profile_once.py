@@ -6,10 +6,11 @@ from fast_lio_b200 import api, synth
 name = sys.argv[1] if len(sys.argv) > 1 else "velodyne_30k_1m"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 solver = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+search = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 pr = synth.make_problem(name)
 t = api.KdTree(0, 0.5)
 t.Build(pr.map_pts)
-f = api.Esekf(t, max_points=len(pr.scan), max_iter=pr.cfg.max_iter, solver=solver)
+f = api.Esekf(t, max_points=len(pr.scan), max_iter=pr.cfg.max_iter, solver=solver, search=search)
 f.upload_scan(pr.scan)
 f.upload_state(pr.x_prior, pr.P_prior, pr.R)
 ms = f.time_resident(reps, flush_l2=True)

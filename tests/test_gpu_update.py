@@ -157,3 +157,17 @@ def test_full_size_properties(problems):
     port = bind.KdTree(pr.map_pts, "port")
     pp, pd, pc = port.knn(q, 5)
     assert np.array_equal(near[idx][:, :, :3], pp[:, :, :3])
+
+
+def test_thread_per_query_search_gives_identical_update(problems):
+    """k_search_t (one thread per scan point) and k_search (one warp per scan point) are interchangeable."""
+    pr = problems("small")
+    t = api.KdTree(0, 0.5); t.Build(pr.map_pts)
+    out = []
+    for search in (0, 1):
+        f = api.Esekf(t, max_points=len(pr.scan), max_iter=pr.cfg.max_iter, search=search)
+        x, P, _ = f.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
+        near, cnt = f.nearest(len(pr.scan))
+        out.append((x, P, near, cnt))
+    assert np.array_equal(out[0][3], out[1][3]) and np.array_equal(out[0][2], out[1][2])
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])

@@ -335,3 +335,4 @@ __device__ __forceinline__ void tknn_query(const MapView& m, float qx, float qy,
 }
 
 }  // namespace fl
+

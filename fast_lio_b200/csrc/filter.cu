@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include <cub/device/device_select.cuh>
 
@@ -26,6 +27,12 @@ constexpr int SEARCH_THREADS = 256;
 constexpr int SEARCH_T_THREADS = 128;
 constexpr int RESID_THREADS = 256;
 constexpr int MAX_LOGS = 16;
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute
+// may start while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor
+// has completed and flushed, pdl_launch() lets the successor begin its own launch early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ int tri12(int a, int b) { return a * 12 - (a * (a - 1)) / 2 + (b - a); }   // a <= b
 
@@ -302,6 +309,8 @@ __device__ __forceinline__ void warp_accumulate(bool contrib, const double* h, d
 // per point.  Runs only when the filter asks for a search (ekfom_data.converge, decided on the
 // device); few registers, so that many warps hide the latency of the dependent tree loads.
 __global__ void __launch_bounds__(SEARCH_THREADS) k_search(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
+    pdl_wait();                 // the previous pass's Kalman step (or the upload) is complete and visible
+    pdl_launch();               // k_residual may start: its solver block prepares while we search
     if (ctl->done || !ctl->converge) return;
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * SEARCH_THREADS + threadIdx.x) >> 5;
@@ -757,6 +766,8 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
 // k_search_t -- the same search with one THREAD per scan point (tknn_query, map.cuh): identical
 // results, ~3x fewer warp instructions per query; a scan is a single wave of threads.
 __global__ void __launch_bounds__(SEARCH_T_THREADS) k_search_t(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
+    pdl_wait();
+    pdl_launch();
     if (ctl->done || !ctl->converge) return;
     const int q = sc.q_begin + blockIdx.x * SEARCH_T_THREADS + threadIdx.x;
     if (q >= sc.q_end) return;
@@ -791,11 +802,15 @@ template <bool EXTR, int SOLVER>
 __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterCtl* ctl, double* __restrict__ partials,
                                                              double* red_g, int mode, PassLog* logs, P2PState* p2p) {
     __shared__ SolveShared S;
+    // ctl was written by the previous pass's k_residual, which completed before this pass's k_search
+    // passed its own pdl_wait(): it may be read before pdl_wait() here
+    pdl_launch();               // the next pass's k_search may queue up (it waits for us at its pdl_wait)
     if (ctl->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = RESID_THREADS / 32;
     const int nwork = (int)gridDim.x - 1;
     if (blockIdx.x > 0) {
+        pdl_wait();             // this pass's k_search has published the neighbours
         const int wb = (int)blockIdx.x - 1;
         const PoseS s = load_pose(ctl->x);
         double acc[3] = {0.0, 0.0, 0.0};
@@ -829,6 +844,7 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
     // ------------------------------------------------------------------ solver block
     STAMP(0);
     if (mode != 1) solve_prepare<SOLVER>(S, ctl);
+    pdl_wait();
     STAMP(8);
     if (threadIdx.x == 0) {
         while (atomicAdd(&ctl->ticket, 0) < nwork) __nanosleep(64);
@@ -899,6 +915,8 @@ template <bool EXTR, int SOLVER>
 __global__ void __launch_bounds__(RESID_THREADS) k_solve_only(FilterCtl* ctl, const double* __restrict__ red_g, ScanView sc,
                                                               PassLog* logs) {
     __shared__ SolveShared S;
+    pdl_wait();
+    pdl_launch();
     if (ctl->done) return;
     solve_prepare<SOLVER>(S, ctl);
     if (threadIdx.x < NRED) S.red[threadIdx.x] = red_g[threadIdx.x];
@@ -1002,6 +1020,7 @@ Filter::~Filter() {
 
 int Filter::init() {
     FL_CUDA(cudaSetDevice(map_->device()));
+    if (const char* e = getenv("FASTLIO_B200_NO_PDL")) pdl_ = !(e[0] == '1');      // A/B switch for tuning
     FL_CHECK(ctl_.reserve(sizeof(FilterCtl)));
     FL_CHECK(ctl0_.reserve(sizeof(FilterCtl)));
     FL_CHECK(red_.reserve(sizeof(double) * PSTRIDE));
@@ -1118,18 +1137,28 @@ int Filter::run_passes() {
     return FL_OK;
 }
 
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 int Filter::launch_search_only() {
     FL_CUDA(cudaSetDevice(map_->device()));
     const int nq = scan_.q_end - scan_.q_begin;
     if (search_mode_ == 1) {
         const int tgrid = std::max(1, (nq + SEARCH_T_THREADS - 1) / SEARCH_T_THREADS);
-        k_search_t<<<tgrid, SEARCH_T_THREADS, 0, stream()>>>(map_->view(), scan_, ctl_.as<FilterCtl>());
-        FL_CUDA(cudaGetLastError());
+        FL_CUDA(launch_pdl(k_search_t, tgrid, SEARCH_T_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
         return FL_OK;
     }
     const int sgrid = std::max(1, std::min(search_grid_max_, (nq * 32 + SEARCH_THREADS - 1) / SEARCH_THREADS));
-    k_search<<<sgrid, SEARCH_THREADS, 0, stream()>>>(map_->view(), scan_, ctl_.as<FilterCtl>());
-    FL_CUDA(cudaGetLastError());
+    FL_CUDA(launch_pdl(k_search, sgrid, SEARCH_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
     return FL_OK;
 }
 int Filter::launch_residual_only() {
@@ -1142,11 +1171,11 @@ int Filter::launch_residual_only() {
     FilterCtl* c = ctl_.as<FilterCtl>(); double* pp = partials_.as<double>(); double* rg = red_.as<double>(); PassLog* lg = logs_.as<PassLog>();
     cudaStream_t st = stream();
     if (extrinsic_est_) {
-        if (solver_) k_residual<true, 1><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg, p2p);
-        else k_residual<true, 0><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg, p2p);
+        if (solver_) FL_CUDA(launch_pdl(k_residual<true, 1>, resid_grid_, RESID_THREADS, st, pdl_, scan_, c, pp, rg, mode, lg, p2p));
+        else FL_CUDA(launch_pdl(k_residual<true, 0>, resid_grid_, RESID_THREADS, st, pdl_, scan_, c, pp, rg, mode, lg, p2p));
     } else {
-        if (solver_) k_residual<false, 1><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg, p2p);
-        else k_residual<false, 0><<<resid_grid_, RESID_THREADS, 0, st>>>(scan_, c, pp, rg, mode, lg, p2p);
+        if (solver_) FL_CUDA(launch_pdl(k_residual<false, 1>, resid_grid_, RESID_THREADS, st, pdl_, scan_, c, pp, rg, mode, lg, p2p));
+        else FL_CUDA(launch_pdl(k_residual<false, 0>, resid_grid_, RESID_THREADS, st, pdl_, scan_, c, pp, rg, mode, lg, p2p));
     }
     FL_CUDA(cudaGetLastError());
     return FL_OK;

@@ -68,6 +68,7 @@ public:
     int init();
     int set_params(int max_iter, const double* limit23, int extrinsic_est_en);
     void set_search_mode(int mode) { search_mode_ = mode; }
+    void set_pdl(bool on) { pdl_ = on; }
     void set_solver(int mode) { solver_ = mode; }       // 1 (default): one ne x ne solve; 0: the reference's two 23x23 inversions, literally
 
     // whole update with host buffers (scan H2D, state H2D, passes, state D2H)
@@ -112,6 +113,7 @@ private:
     double limit_[NDOF];
     int extrinsic_est_ = 0;
     int solver_ = 1;
+    bool pdl_ = true;                  // programmatic dependent launch between the kernels of a scan
     int search_mode_ = 0;              // 0: one warp per query (k_search, default); 1: one thread per query (k_search_t, measured 2.8x slower)
     ScanView scan_;
     DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, partials_, red_, ctl_, ctl0_, logs_;

@@ -113,6 +113,28 @@ def algorithmic_bytes_search(n_map: int, k: int = 5) -> int:
     return 16 + 32 * math.ceil(math.log2(max(2, n_map))) + 32 * k
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def c_stdout_to_stderr():
+    """The reference's ikd_Tree.cpp printf()s to stdout (ikd_Tree.cpp:202,365); bench.py's stdout must carry
+    exactly one JSON line, so file descriptor 1 points at stderr while the CPU oracle runs."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def cpu_update_loop(pr, n_scans: int, nthreads: int, warm: int = 1):
     """Times the CPU reference path.  The reference's OpenMP loop (laserMapping.cpp:646-650) does not
     scale to every core count (allocation inside KD_TREE::Nearest_Search), so the thread count is
@@ -152,7 +174,8 @@ def run_reference(args, rank: int):
     from fast_lio_b200 import synth
     pr = synth.make_problem(args.workload)
     cores = os.cpu_count() or 1
-    times, kind, cores = cpu_update_loop(pr, args.steps, cores, warm=max(1, args.warmup))
+    with c_stdout_to_stderr():
+        times, kind, cores = cpu_update_loop(pr, args.steps, cores, warm=max(1, args.warmup))
     total = float(np.sum(times))
     val = len(times) / total
     line = {
@@ -272,7 +295,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n_cpu = max(3, min(40, args.cpu_scans))
-            times, kind, cores = cpu_update_loop(pr, n_cpu, cores, warm=1)
+            with c_stdout_to_stderr():
+                times, kind, cores = cpu_update_loop(pr, n_cpu, cores, warm=1)
             cpu = {"value": len(times) / float(np.sum(times)), "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": f"{len(times)} full scan updates of the same workload (median {1e3 * float(np.median(times)):.1f} ms/scan), thread count calibrated"}
         line = {

@@ -44,6 +44,8 @@ SYMBOLS = [
     "fl_filter_map_incremental", "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
     "fl_filter_upload_state", "fl_filter_run", "fl_filter_download_state", "fl_filter_sync",
     "fl_filter_time_resident", "fl_filter_time_search_pass", "fl_filter_gpu_launches",
+    "fl_scan_create", "fl_scan_destroy", "fl_scan_upload", "fl_scan_undistort", "fl_scan_voxel_downsample", "fl_scan_download",
+    "fl_filter_update_scan", "fl_localmap_create", "fl_localmap_destroy", "fl_localmap_segment", "fl_localmap_get",
     "fl_comm_unique_id", "fl_filter_comm_init", "fl_filter_set_shard", "fl_filter_p2p_handle", "fl_filter_p2p_connect",
 ]
 
@@ -95,6 +97,17 @@ def load():
     L.fl_filter_time_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.fl_filter_time_search_pass.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.fl_filter_gpu_launches.argtypes = [C.c_void_p]
+    L.fl_scan_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p]
+    L.fl_scan_destroy.argtypes = [C.c_void_p]
+    L.fl_scan_upload.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int]
+    L.fl_scan_undistort.argtypes = [C.c_void_p, _f64p, C.c_int, _f64p]
+    L.fl_scan_voxel_downsample.argtypes = [C.c_void_p, C.c_float]
+    L.fl_scan_download.argtypes = [C.c_void_p, C.c_int, _f32p, C.c_int]
+    L.fl_filter_update_scan.argtypes = [C.c_void_p, C.c_void_p, _f64p, _f64p, C.c_double, C.POINTER(C.c_double)]
+    L.fl_localmap_create.argtypes = [C.POINTER(C.c_void_p), C.c_double, C.c_float]
+    L.fl_localmap_destroy.argtypes = [C.c_void_p]
+    L.fl_localmap_segment.argtypes = [C.c_void_p, C.c_void_p, _f64p, _f32p, C.POINTER(C.c_int)]
+    L.fl_localmap_get.argtypes = [C.c_void_p, _f32p]
     L.fl_comm_unique_id.argtypes = [C.c_char_p]
     L.fl_filter_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
     L.fl_filter_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -299,6 +312,92 @@ class Esekf:
 
     def set_shard(self, q_begin: int, q_end: int):
         _check(self._L.fl_filter_set_shard(self.h, q_begin, q_end))
+
+
+class Scan:
+    """feats_undistort / feats_down_body kept in HBM: UndistortPcl's backward pass (IMU_Processing.hpp:232-346) and the
+    pcl::VoxelGrid down-sampling (laserMapping.cpp:904-905) in front of the update."""
+
+    def __init__(self, tree: KdTree):
+        self._L = load()
+        self.tree = tree
+        h = C.c_void_p()
+        _check(self._L.fl_scan_create(C.byref(h), tree.h))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.fl_scan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, xyzi, offset_ms):
+        xyzi = np.ascontiguousarray(xyzi, dtype=np.float32).reshape(-1, 4)
+        offset_ms = np.ascontiguousarray(offset_ms, dtype=np.float32).reshape(-1)
+        if len(offset_ms) != len(xyzi):
+            raise ValueError("one offset time per point")
+        _check(self._L.fl_scan_upload(self.h, xyzi, offset_ms, len(xyzi)))
+        self.n = len(xyzi)
+
+    def undistort(self, imu_pose22, x26_end):
+        poses = np.ascontiguousarray(imu_pose22, dtype=np.float64).reshape(-1, 22)
+        _check(self._L.fl_scan_undistort(self.h, poses, len(poses), np.ascontiguousarray(x26_end, dtype=np.float64)))
+
+    def voxel_downsample(self, leaf: float) -> int:
+        return _check(self._L.fl_scan_voxel_downsample(self.h, leaf))
+
+    def download(self, which: int = 1) -> np.ndarray:
+        n = _check(self._L.fl_scan_download(self.h, which, np.zeros((1, 4), dtype=np.float32), 0))
+        out = np.zeros((max(n, 1), 4), dtype=np.float32)
+        _check(self._L.fl_scan_download(self.h, which, out, n))
+        return out[:n].copy()
+
+    def update(self, filt: "Esekf", x26, P, R: float = 0.001):
+        """fl_filter_update on the down-sampled cloud without a host hop; returns (x, P, solve_time_s)."""
+        x = np.array(x26, dtype=np.float64).copy()
+        Pm = np.ascontiguousarray(np.array(P, dtype=np.float64).copy())
+        st = C.c_double(0.0)
+        _check(self._L.fl_filter_update_scan(filt.h, self.h, x, Pm, R, C.byref(st)))
+        return x, Pm, st.value
+
+
+class LocalMap:
+    """lasermap_fov_segment() (laserMapping.cpp:229-277): the sliding cube that issues the delete boxes."""
+
+    def __init__(self, cube_len: float, det_range: float):
+        self._L = load()
+        h = C.c_void_p()
+        _check(self._L.fl_localmap_create(C.byref(h), cube_len, det_range))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.fl_localmap_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def segment(self, pos_lid, tree: "KdTree | None" = None):
+        """Returns (cub_needrm as an (nb, 6) array, kdtree_delete_counter)."""
+        boxes = np.zeros((3, 6), dtype=np.float32)
+        nd = C.c_int(0)
+        nb = _check(self._L.fl_localmap_segment(self.h, tree.h if tree is not None else None,
+                                                np.ascontiguousarray(pos_lid, dtype=np.float64), boxes, C.byref(nd)))
+        return boxes[:nb].copy(), nd.value
+
+    def box(self) -> np.ndarray:
+        b = np.zeros(6, dtype=np.float32)
+        _check(self._L.fl_localmap_get(self.h, b))
+        return b
 
 
 def host_register(arr: np.ndarray):

@@ -5,6 +5,7 @@
 
 #include "../../include/fastlio_b200.h"
 #include "filter.h"
+#include "scan.h"
 
 namespace fl {
 const char* last_error();
@@ -19,6 +20,14 @@ struct fl_filter {
     fl::Filter* impl;
     fl_map* map;
     fl::DeviceBuffer flush;
+};
+
+struct fl_scan {
+    fl::ScanFrontEnd* impl;
+    fl_map* map;
+};
+struct fl_localmap {
+    fl::LocalMapCube cube;
 };
 
 static_assert(sizeof(fl_pass_log_t) == sizeof(fl::PassLog), "pass-log layouts must match");
@@ -232,6 +241,85 @@ int fl_filter_time_search_pass(fl_filter_t* f, int reps, int flush_l2, float* ms
     // leave the control block as uploaded
     FL_CHECK(F->restore_state());
     *ms_total = total;
+    return FL_OK;
+}
+
+// ------------------------------------------------------------------------------------ scan front end
+#define SCAN_GUARD(s)                                                                        \
+    if (!(s) || !(s)->impl) { fl::set_last_error("null scan handle"); return FL_ERR_ARG; }   \
+    std::lock_guard<std::mutex> _lk((s)->map->mu)
+
+int fl_scan_create(fl_scan_t** out, fl_map_t* map) {
+    if (!out) return FL_ERR_ARG;
+    *out = nullptr;
+    if (!map || !map->impl) { fl::set_last_error("fl_scan_create: null map handle"); return FL_ERR_ARG; }
+    fl_scan* s = new (std::nothrow) fl_scan();
+    if (!s) return FL_ERR_CAPACITY;
+    s->map = map;
+    s->impl = new (std::nothrow) fl::ScanFrontEnd(map->impl);
+    if (!s->impl) { delete s; return FL_ERR_CAPACITY; }
+    int rc = s->impl->init();
+    if (rc != FL_OK) { delete s->impl; delete s; return rc; }
+    *out = s;
+    return FL_OK;
+}
+int fl_scan_destroy(fl_scan_t* s) {
+    if (!s) return FL_OK;
+    delete s->impl;
+    delete s;
+    return FL_OK;
+}
+int fl_scan_upload(fl_scan_t* s, const float* xyzi, const float* offset_ms, int n) { SCAN_GUARD(s); return s->impl->upload(xyzi, offset_ms, n); }
+int fl_scan_undistort(fl_scan_t* s, const double* imu_pose22, int n_pose, const double* x26_end) {
+    SCAN_GUARD(s);
+    return s->impl->undistort(imu_pose22, n_pose, x26_end);
+}
+int fl_scan_voxel_downsample(fl_scan_t* s, float leaf_size) {
+    SCAN_GUARD(s);
+    int n = 0;
+    int rc = s->impl->voxel_downsample(leaf_size, &n);
+    return rc == FL_OK ? n : rc;
+}
+int fl_scan_download(fl_scan_t* s, int which, float* out_xyzi, int cap) {
+    SCAN_GUARD(s);
+    int n = 0;
+    int rc = s->impl->download(which, out_xyzi, cap, &n);
+    return rc == FL_OK ? n : rc;
+}
+int fl_filter_update_scan(fl_filter_t* f, fl_scan_t* s, double* x26, double* P, double R, double* solve_time_s) {
+    FILTER_GUARD(f);
+    if (!s || !s->impl || s->map != f->map) { fl::set_last_error("fl_filter_update_scan: the scan must live on the filter's map"); return FL_ERR_ARG; }
+    return f->impl->update_device(s->impl->down_device(), s->impl->down_count(), x26, P, R, solve_time_s);
+}
+
+// ------------------------------------------------------------------------------------ local-map cube
+int fl_localmap_create(fl_localmap_t** out, double cube_len, float det_range) {
+    if (!out) return FL_ERR_ARG;
+    *out = nullptr;
+    if (!(cube_len > 0.0) || !(det_range > 0.f)) { fl::set_last_error("fl_localmap_create: cube_len and det_range must be > 0"); return FL_ERR_ARG; }
+    fl_localmap* l = new (std::nothrow) fl_localmap{fl::LocalMapCube(cube_len, det_range)};
+    if (!l) return FL_ERR_CAPACITY;
+    *out = l;
+    return FL_OK;
+}
+int fl_localmap_destroy(fl_localmap_t* l) { delete l; return FL_OK; }
+int fl_localmap_segment(fl_localmap_t* l, fl_map_t* map, const double* pos_lid, float* boxes6_out, int* n_deleted) {
+    if (n_deleted) *n_deleted = 0;
+    if (!l || !pos_lid) { fl::set_last_error("fl_localmap_segment: null argument"); return FL_ERR_ARG; }
+    float boxes[18];
+    const int nb = l->cube.slide(pos_lid, boxes);
+    if (boxes6_out) for (int i = 0; i < nb * 6; i++) boxes6_out[i] = boxes[i];
+    if (nb > 0 && map) {                              // if (cub_needrm.size() > 0) ikdtree.Delete_Point_Boxes(cub_needrm)  (:275)
+        int deleted = fl_map_delete_boxes(map, boxes, nb);
+        if (deleted < 0) return deleted;
+        if (n_deleted) *n_deleted = deleted;
+    }
+    return nb;
+}
+int fl_localmap_get(fl_localmap_t* l, float* box6) {
+    if (!l || !box6) return FL_ERR_ARG;
+    if (!l->cube.initialized()) { fl::set_last_error("fl_localmap_get: the cube is placed by the first fl_localmap_segment call"); return FL_ERR_STATE; }
+    l->cube.get(box6);
     return FL_OK;
 }
 

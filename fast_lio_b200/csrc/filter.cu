@@ -1203,11 +1203,19 @@ int Filter::download_state(double* x26, double* P, int* n_pass) {
 }
 
 int Filter::update(const float* body_xyzi, int nq, double* x26, double* P, double R, double* solve_time_s) {
+    return update_any(body_xyzi, nullptr, nq, x26, P, R, solve_time_s);
+}
+int Filter::update_device(const float4* d_body, int nq, double* x26, double* P, double R, double* solve_time_s) {
+    if (nq > 0 && !d_body) { set_last_error("update: null device scan"); return FL_ERR_ARG; }
+    return update_any(nullptr, d_body, nq, x26, P, R, solve_time_s);
+}
+int Filter::update_any(const float* body_xyzi, const float4* d_body, int nq, double* x26, double* P, double R, double* solve_time_s) {
     if (!x26 || !P) { set_last_error("update: null state"); return FL_ERR_ARG; }
     FL_CUDA(cudaSetDevice(map_->device()));
     if (solve_time_s && !ev0_) { FL_CUDA(cudaEventCreate(&ev0_)); FL_CUDA(cudaEventCreate(&ev1_)); }
     if (solve_time_s) FL_CUDA(cudaEventRecord(ev0_, stream()));
-    FL_CHECK(upload_scan(body_xyzi, nq));
+    if (d_body) FL_CHECK(set_scan_device(d_body, nq));
+    else FL_CHECK(upload_scan(body_xyzi, nq));
     FL_CHECK(upload_state(x26, P, R, false));
     FL_CHECK(run_passes());
     if (solve_time_s) FL_CUDA(cudaEventRecord(ev1_, stream()));

@@ -73,6 +73,8 @@ public:
 
     // whole update with host buffers (scan H2D, state H2D, passes, state D2H)
     int update(const float* body_xyzi, int nq, double* x26, double* P, double R, double* solve_time_s);
+    // same with feats_down_body already in HBM on the map's device (ScanFrontEnd::down_device())
+    int update_device(const float4* d_body, int nq, double* x26, double* P, double R, double* solve_time_s);
     // pieces, for device-resident benchmarking / pipelines
     int upload_scan(const float* body_xyzi, int nq);
     int set_scan_device(const float4* d_body, int nq);
@@ -107,6 +109,7 @@ public:
 
 private:
     int reserve(int nq);
+    int update_any(const float* body_xyzi, const float4* d_body, int nq, double* x26, double* P, double R, double* solve_time_s);
     Map* map_;
     int max_points_;
     int max_iter_ = 4;

@@ -319,6 +319,86 @@ def make_scan(scene: Scene, n_scan: int, x_true: np.ndarray, seed: int = 2, nois
 
 
 @dataclasses.dataclass
+class RawScan:
+    xyzi: np.ndarray         # n x 4 float32, body (LiDAR) frame AT EACH POINT'S OWN TIME, acquisition order
+    offset_ms: np.ndarray    # n float32, PointType::curvature (offset from the first point, milliseconds)
+    imu_pose: np.ndarray     # n_pose x 22 float64, IMUpose (msg/Pose6D.msg), offsets in seconds
+    x_end: np.ndarray        # 26, state at the frame end
+    truth_end: np.ndarray    # n x 3 float64: the same surface points in the LiDAR frame at the frame end
+
+
+def make_raw_scan(scene: Scene, n_raw: int, x_end: np.ndarray, seed: int = 5, period_s: float = 0.1, imu_hz: float = 200.0,
+                  omega=(0.3, -0.2, 0.8), accel=(0.4, -0.3, 0.1), noise_sigma: float = 0.0, shuffle: bool = True) -> RawScan:
+    """A raw (not yet de-skewed, not yet down-sampled) scan of `scene` taken by a sensor that moves with constant
+    body-frame angular velocity `omega` and constant world acceleration `accel` during `period_s`, ending in `x_end`.
+    That is the motion model of UndistortPcl's backward pass (IMU_Processing.hpp:327-336), so compensating the
+    points with the returned IMUpose list must reproduce `truth_end` up to float32 rounding.  Several points fall into
+    one 0.5 m cell (raw scans are denser than the down-sampled cloud the update consumes)."""
+    rng = np.random.default_rng(seed)
+    omega = np.asarray(omega, dtype=np.float64)
+    accel = np.asarray(accel, dtype=np.float64)
+    T = float(period_s)
+    R_end = quat_to_mat(x_end[3:7])
+    p_end = np.array(x_end[0:3], dtype=np.float64)
+    v_end = np.array(x_end[14:17], dtype=np.float64)
+    R_li = quat_to_mat(x_end[7:11])
+    t_li = np.array(x_end[11:14], dtype=np.float64)
+    R0 = R_end @ quat_to_mat(quat_exp(-omega * T))
+    v0 = v_end - accel * T
+    p0 = p_end - v0 * T - 0.5 * accel * T * T
+
+    def pose_at(t):
+        return R0 @ quat_to_mat(quat_exp(omega * t)), p0 + v0 * t + 0.5 * accel * t * t, v0 + accel * t
+
+    # surface points around the end pose, with replacement over cells -> several points per voxel
+    radius = 15.0
+    while True:
+        kind, a, b, c = _enumerate_cells(scene, p_end[0], p_end[1], radius)
+        if len(kind) * 3 >= n_raw or radius > 4 * scene.extent:
+            break
+        radius *= 1.25
+    pick = rng.integers(0, len(kind), size=n_raw)
+    w = _points_from_cells(rng, kind[pick], a[pick], b[pick], c[pick])
+    if noise_sigma > 0:
+        w += rng.normal(0.0, noise_sigma, size=w.shape)
+    t = np.sort(rng.uniform(0.0, T, size=n_raw))
+    t[0] = 0.0                                          # the first point defines the offset origin
+    t_ms = (t * 1000.0).astype(np.float32)
+    t_used = t_ms.astype(np.float64) / 1000.0           # what the de-skew will see
+    xyz = np.empty((n_raw, 3), dtype=np.float64)
+    for lo in range(0, n_raw, 4096):                    # per-point pose, vectorised through Rodrigues
+        tt = t_used[lo:lo + 4096]
+        th = np.linalg.norm(omega)
+        k = omega / th if th > 0 else np.zeros(3)
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        ang = th * tt
+        Rt = R0[None] @ (np.eye(3)[None] + np.sin(ang)[:, None, None] * K[None] + (1 - np.cos(ang))[:, None, None] * (K @ K)[None])
+        pt = p0[None] + v0[None] * tt[:, None] + 0.5 * accel[None] * (tt * tt)[:, None]
+        p_imu = np.einsum("nji,nj->ni", Rt, w[lo:lo + 4096] - pt)          # R(t)^T (w - p(t))
+        xyz[lo:lo + 4096] = (p_imu - t_li) @ R_li
+    truth = ((w - p_end) @ R_end - t_li) @ R_li
+    xyzi = np.empty((n_raw, 4), dtype=np.float32)
+    xyzi[:, :3] = xyz.astype(np.float32)
+    xyzi[:, 3] = rng.uniform(1.0, 100.0, n_raw).astype(np.float32)
+    if shuffle:                                          # drivers deliver points ring by ring, not by time
+        perm = rng.permutation(n_raw)
+        xyzi, t_ms, truth = xyzi[perm], t_ms[perm], truth[perm]
+    # IMUpose: offset 0 first (IMU_Processing.hpp:241), then one entry per IMU sample, the last one at/after the frame end
+    n_imu = int(math.ceil(T * imu_hz))
+    offs = [0.0] + [min(T, (k + 1) / imu_hz) for k in range(n_imu)]
+    poses = np.zeros((len(offs), 22), dtype=np.float64)
+    for k, o in enumerate(offs):
+        Rk, pk, vk = pose_at(o)
+        poses[k, 0] = o
+        poses[k, 1:4] = accel                           # acc: world-frame acceleration of the segment ENDING here (:327)
+        poses[k, 4:7] = omega                           # gyr: unbiased body-frame rate of that segment (:328)
+        poses[k, 7:10] = vk
+        poses[k, 10:13] = pk
+        poses[k, 13:22] = Rk.reshape(-1)
+    return RawScan(np.ascontiguousarray(xyzi), np.ascontiguousarray(t_ms), poses, np.array(x_end, dtype=np.float64).copy(), truth)
+
+
+@dataclasses.dataclass
 class Problem:
     cfg: Config
     map_pts: np.ndarray      # N x 4 float32

@@ -128,6 +128,41 @@ int fl_filter_gpu_launches(fl_filter_t* f);
 /* clock64() stamps of the last on-device Kalman step (tuning aid; layout in scripts/profile_once.py) */
 int fl_filter_debug_prof(fl_filter_t* f, long long* out16);
 
+/* ------------------------------------------------------------------ scan front end
+ * The two steps that produce feats_down_body, kept in HBM on the map's device and stream so that a scan goes
+ * raw -> de-skewed -> down-sampled -> update -> map_incremental with one upload. */
+typedef struct fl_scan fl_scan_t;      /* replaces the feats_undistort / feats_down_body clouds   laserMapping.cpp:122-124 */
+int fl_scan_create(fl_scan_t** out, fl_map_t* map);
+int fl_scan_destroy(fl_scan_t* s);
+/* Measures.lidar (common_lib.h:47-58): n x (x,y,z,intensity) + PointType::curvature = offset time in ms */
+int fl_scan_upload(fl_scan_t* s, const float* xyzi, const float* offset_ms, int n);
+/* ImuProcess::UndistortPcl, the sort (:234) and the backward pass (:312-346)         IMU_Processing.hpp:216-346
+ * imu_pose22: IMUpose, n_pose x Pose6D (msg/Pose6D.msg: offset_time, acc[3], gyr[3], vel[3], pos[3], rot[9] row-major),
+ * filled by the caller's forward propagation (:244-301, esekf::predict stays on the host);
+ * x26_end: kf_state.get_x() after the last predict (:303).  Points stay in HBM, time-sorted (stable). */
+int fl_scan_undistort(fl_scan_t* s, const double* imu_pose22, int n_pose, const double* x26_end);
+/* downSizeFilterSurf.setInputCloud(feats_undistort); .filter(*feats_down_body)         laserMapping.cpp:904-905
+ * = pcl::VoxelGrid<PointType> with leaf (l,l,l) (laserMapping.cpp:811): centroid of every occupied cell, output in
+ * ascending cell index.  Returns feats_down_size (>= 0) or an error (< 0). */
+int fl_scan_voxel_downsample(fl_scan_t* s, float leaf_size);
+/* which 0: the raw / de-skewed cloud, 1: the down-sampled cloud; returns the cloud's size (writes at most cap points) */
+int fl_scan_download(fl_scan_t* s, int which, float* out_xyzi, int cap);
+/* fl_filter_update on the down-sampled cloud of `s` without a host hop */
+int fl_filter_update_scan(fl_filter_t* f, fl_scan_t* s, double* x26, double* P, double R, double* solve_time_s);
+
+/* ------------------------------------------------------------------ local-map cube
+ * lasermap_fov_segment()                                            laserMapping.cpp:229-277
+ * LocalMap_Points / Localmap_Initialized (:229-230) live in the handle; cube_len = cube_side_length (:774),
+ * det_range = mapping/det_range (:775). */
+typedef struct fl_localmap fl_localmap_t;
+int fl_localmap_create(fl_localmap_t** out, double cube_len, float det_range);
+int fl_localmap_destroy(fl_localmap_t* l);
+/* One call per scan with pos_lid (:236).  Returns |cub_needrm| (0..3); boxes6_out (may be NULL, room for 3 boxes)
+ * receives cub_needrm; with map != NULL also runs ikdtree.Delete_Point_Boxes(cub_needrm) (:275) and stores
+ * kdtree_delete_counter in *n_deleted (may be NULL). */
+int fl_localmap_segment(fl_localmap_t* l, fl_map_t* map, const double* pos_lid, float* boxes6_out, int* n_deleted);
+int fl_localmap_get(fl_localmap_t* l, float* box6);   /* LocalMap_Points as (min xyz, max xyz) */
+
 /* ------------------------------------------------------------------ multi-GPU (no reference counterpart)
  * scan points are sharded across ranks, the map is replicated, the 92 normal-equation doubles
  * are all-reduced once per pass (NCCL over NVLink) and every rank solves redundantly. */

@@ -35,9 +35,15 @@ class PassLog(C.Structure):
                 ("x_after", C.c_double * 26)]
 
 
+class LocalMapState(C.Structure):
+    _fields_ = [("vmin", C.c_float * 3), ("vmax", C.c_float * 3), ("initialized", C.c_int)]
+
+
 def build(force: bool = False) -> None:
     """Compile oracle/liboracle.so and, when /root/reference is present, oracle/_ref."""
-    if force or not os.path.exists(LIB_PATH) or (os.path.isdir("/root/reference") and not os.path.exists(REF_PATH)):
+    srcs = [os.path.join(HERE, f) for f in ("fastlio_oracle.cpp", "knn_port.cpp", "frontend_oracle.cpp")]
+    stale = os.path.exists(LIB_PATH) and any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs)
+    if force or stale or not os.path.exists(LIB_PATH) or (os.path.isdir("/root/reference") and not os.path.exists(REF_PATH)):
         subprocess.check_call(["make", "-C", HERE], stdout=subprocess.DEVNULL)
 
 
@@ -66,6 +72,12 @@ def lib():
         L.port_kdtree_build.restype = C.c_void_p
         L.port_kdtree_destroy.argtypes = [C.c_void_p]
         L.port_kdtree_knn.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, _f32p, _f32p, _i32p, C.c_int]
+        L.oracle_fov_segment.argtypes = [C.POINTER(LocalMapState), _f64p, C.c_double, C.c_float, _f32p]
+        L.oracle_fov_segment.restype = C.c_int
+        L.oracle_undistort.argtypes = [_f32p, _f32p, C.c_int, _f64p, C.c_int, _f64p]
+        L.oracle_undistort.restype = None
+        L.oracle_voxelgrid.argtypes = [_f32p, C.c_int, C.c_float, _f32p]
+        L.oracle_voxelgrid.restype = C.c_int
         _lib = L
     return _lib
 
@@ -206,3 +218,38 @@ def esti_plane(pts5x3, threshold=0.1):
     out = np.zeros(4, dtype=np.float32)
     ok = lib().oracle_esti_plane(np.ascontiguousarray(pts5x3, dtype=np.float32).reshape(-1), threshold, out)
     return bool(ok), out
+
+
+class LocalMap:
+    """lasermap_fov_segment (laserMapping.cpp:229-277) restated; one segment() per scan."""
+
+    def __init__(self, cube_len: float, det_range: float):
+        self.st = LocalMapState()
+        self.cube_len, self.det_range = float(cube_len), float(det_range)
+
+    def segment(self, pos_lid) -> np.ndarray:
+        boxes = np.zeros((3, 6), dtype=np.float32)
+        nb = lib().oracle_fov_segment(C.byref(self.st), np.ascontiguousarray(pos_lid, dtype=np.float64), self.cube_len, self.det_range, boxes)
+        return boxes[:nb].copy()
+
+    def box(self) -> np.ndarray:
+        return np.array(list(self.st.vmin) + list(self.st.vmax), dtype=np.float32)
+
+
+def undistort(xyzi, offset_ms, imu_pose22, x26_end):
+    """UndistortPcl: stable sort by offset time (IMU_Processing.hpp:234) + backward pass (:312-346).  Returns (pts, t)."""
+    xyzi = np.ascontiguousarray(xyzi, dtype=np.float32).reshape(-1, 4)
+    t = np.ascontiguousarray(offset_ms, dtype=np.float32).reshape(-1)
+    order = np.argsort(t, kind="stable")
+    pts, ts = np.ascontiguousarray(xyzi[order]), np.ascontiguousarray(t[order])
+    poses = np.ascontiguousarray(imu_pose22, dtype=np.float64).reshape(-1, 22)
+    lib().oracle_undistort(pts, ts, len(pts), poses, len(poses), np.ascontiguousarray(x26_end, dtype=np.float64))
+    return pts, ts
+
+
+def voxelgrid(xyzi, leaf: float) -> np.ndarray:
+    """pcl::VoxelGrid::filter as called at laserMapping.cpp:904-905 (restated; see frontend_oracle.cpp)."""
+    xyzi = np.ascontiguousarray(xyzi, dtype=np.float32).reshape(-1, 4)
+    out = np.zeros((max(len(xyzi), 1), 4), dtype=np.float32)
+    n = lib().oracle_voxelgrid(xyzi, len(xyzi), leaf, out)
+    return out[:n].copy()

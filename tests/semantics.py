@@ -116,3 +116,33 @@ def map_incremental(scan4, x26, nearest, nearest_cnt, fsm=0.5, ekf_inited=True):
         else:
             to_add.append(pw)
     return (np.array(to_add, dtype=np.float32).reshape(-1, 4), np.array(no_need, dtype=np.float32).reshape(-1, 4))
+
+
+def voxelgrid_model(pts4, leaf):
+    """pcl::VoxelGrid::applyFilter (PCL 1.8-1.12, pcl/filters/impl/voxel_grid.hpp) in numpy float32, written
+    independently of oracle/frontend_oracle.cpp: bounding box -> min_b/div_b -> cell index -> stable sort ->
+    sequential float32 centroid per cell, cells in ascending index."""
+    f32 = np.float32
+    pts = np.asarray(pts4, dtype=f32).reshape(-1, 4)
+    if len(pts) == 0:
+        return pts.copy()
+    inv = f32(1.0) / f32(leaf)
+    mn, mx = pts[:, :3].min(axis=0), pts[:, :3].max(axis=0)
+    d = [int(f32(f32(mx[c] - mn[c]) * inv)) + 1 for c in range(3)]
+    if d[0] * d[1] * d[2] > 2 ** 31 - 1:
+        return pts.copy()
+    min_b = np.floor(mn * inv).astype(np.int32)
+    div = np.floor(mx * inv).astype(np.int32) - min_b + 1
+    ijk = (np.floor(pts[:, :3] * inv) - min_b.astype(f32)).astype(np.int32)
+    idx = (ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]).astype(np.uint32)
+    order = np.argsort(idx, kind="stable")
+    sidx = idx[order]
+    starts = np.flatnonzero(np.r_[True, sidx[1:] != sidx[:-1]])
+    ends = np.r_[starts[1:], len(sidx)]
+    out = np.zeros((len(starts), 4), dtype=f32)
+    for k, (a, b) in enumerate(zip(starts, ends)):
+        s = np.zeros(4, dtype=f32)
+        for j in order[a:b]:
+            s = s + pts[j]
+        out[k] = s / f32(b - a)
+    return out

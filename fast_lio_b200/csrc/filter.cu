@@ -210,17 +210,26 @@ __device__ __forceinline__ void jacobian_row(const PoseS& s, const float4& pb, c
 // Per-point part of h_share_model after the search (laserMapping.cpp:674-692).
 // Returns true when the point contributes a row.
 template <bool EXTR>
-__device__ __forceinline__ bool measure_point(const ScanView& sc, int q, const PoseS& s, double* h, double& z, float& absres) {
+__device__ __forceinline__ bool measure_point(const ScanView& sc, int q, const PoseS& s, bool searched, double* h, double& z, float& absres) {
     if (!sc.selected[q]) return false;                                   // :674
     sc.selected[q] = 0;                                                  // :677
     const float4 pb = __ldg(&sc.body[q]);
     float wx, wy, wz;
     body_to_world(s, pb, wx, wy, wz);
-    float pn[KNN_K][3];
-#pragma unroll
-    for (int j = 0; j < KNN_K; j++) { const float4 p = sc.nearest[(size_t)q * KNN_K + j]; pn[j][0] = p.x; pn[j][1] = p.y; pn[j][2] = p.z; }
     float pabcd[4];
-    if (!esti_plane_dev(pabcd, pn, 0.1f)) return false;                  // :678
+    if (searched) {
+        float pn[KNN_K][3];
+#pragma unroll
+        for (int j = 0; j < KNN_K; j++) { const float4 p = sc.nearest[(size_t)q * KNN_K + j]; pn[j][0] = p.x; pn[j][1] = p.y; pn[j][2] = p.z; }
+        if (!esti_plane_dev(pabcd, pn, 0.1f)) return false;              // :678
+        sc.plane[q] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
+    } else {
+        // A pass that does not search fits the plane to the SAME five neighbours (Nearest_Points persists, T3) and
+        // only points whose fit succeeded last time are still selected: the fit is a pure function of the
+        // neighbours, so its result is reused instead of recomputed.
+        const float4 pl = sc.plane[q];
+        pabcd[0] = pl.x; pabcd[1] = pl.y; pabcd[2] = pl.z; pabcd[3] = pl.w;
+    }
     const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];          // :680
     const D3 p_body = d3(pb.x, pb.y, pb.z);
     const float score = (float)(1 - 0.9 * fabs((double)pd2) / sqrt(norm3(p_body)));     // :681 (T8)
@@ -813,6 +822,7 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
         pdl_wait();             // this pass's k_search has published the neighbours
         const int wb = (int)blockIdx.x - 1;
         const PoseS s = load_pose(ctl->x);
+        const bool searched = ctl->converge != 0;      // what this pass's k_search saw (laserMapping.cpp:667)
         double acc[3] = {0.0, 0.0, 0.0};
         // worker blocks do not use the solver's matrices: their storage stages the warps' rows
         constexpr int STAGE = 32 * RowStage<EXTR>::RS + 96;
@@ -823,7 +833,7 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
             const int q = base + lane;
             double h[12]; double z = 0.0; float ar = 0.f;
             bool contrib = false;
-            if (q < q1) contrib = measure_point<EXTR>(sc, q, s, h, z, ar);
+            if (q < q1) contrib = measure_point<EXTR>(sc, q, s, searched, h, z, ar);
             warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane, stage);
         }
         double (*wacc)[PSTRIDE] = reinterpret_cast<double (*)[PSTRIDE]>(S.wred);     // NW x 96 doubles
@@ -1010,7 +1020,7 @@ Filter::~Filter() {
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     for (int r = 0; r < P2P_MAX_RANKS; r++) if (peer_ptr_[r]) cudaIpcCloseMemHandle(peer_ptr_[r]);
     mailbox_.release(); p2p_.release();
-    body_.release(); nearest_.release(); nearest_cnt_.release(); selected_.release(); normvec_.release();
+    body_.release(); nearest_.release(); nearest_cnt_.release(); selected_.release(); normvec_.release(); plane_.release();
     partials_.release(); red_.release(); ctl_.release(); ctl0_.release(); logs_.release();
     mi_world_.release(); mi_flag_add_.release(); mi_flag_no_.release(); mi_list_add_.release(); mi_list_no_.release(); mi_tmp_.release(); mi_counts_.release();
     if (h_ctl_) cudaFreeHost(h_ctl_);
@@ -1052,6 +1062,8 @@ int Filter::reserve(int nq) {
     scan_.nearest_cnt = nearest_cnt_.as<int>();
     scan_.selected = selected_.as<unsigned char>();
     scan_.normvec = normvec_.as<float4>();
+    FL_CHECK(plane_.reserve(sizeof(float4) * (size_t)nq));
+    scan_.plane = plane_.as<float4>();
     return FL_OK;
 }
 

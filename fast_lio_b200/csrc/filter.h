@@ -45,6 +45,7 @@ struct ScanView {
     int* nearest_cnt;        // [Q]
     unsigned char* selected; // [Q] point_selected_surf (persists across passes, trap T3)
     float4* normvec;         // [Q] (n, pd2)                                    normvec
+    float4* plane;           // [Q] pabcd of the last search pass's plane fit (reused by the passes that do not search)
     int q_begin, q_end;      // this rank's shard of the scan
     int Q;
 };
@@ -119,7 +120,7 @@ private:
     bool pdl_ = true;                  // programmatic dependent launch between the kernels of a scan
     int search_mode_ = 0;              // 0: one warp per query (k_search, default); 1: one thread per query (k_search_t, measured 2.8x slower)
     ScanView scan_;
-    DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, partials_, red_, ctl_, ctl0_, logs_;
+    DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, plane_, partials_, red_, ctl_, ctl0_, logs_;
     DeviceBuffer mi_world_, mi_flag_add_, mi_flag_no_, mi_list_add_, mi_list_no_, mi_tmp_, mi_counts_;
     FilterCtl* h_ctl_ = nullptr;       // pinned staging
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

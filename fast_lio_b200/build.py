@@ -44,7 +44,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-ldl"]
+    tmp = LIB + ".tmp"          # link into a temporary, then rename: a snapshot of the tree never sees a half-written library
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-ccbin", "/usr/bin/g++"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp, "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
@@ -52,6 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed")
+    os.replace(tmp, LIB)
     if verbose:
         print(log)
     return LIB

@@ -67,22 +67,33 @@ public:
     void update_iterated_dyn_share_modified(double R, double& solve_time) {
         if (!filter_) { base::update_iterated_dyn_share_modified(R, solve_time); return; }   // not bound: the reference's own path
         double x[26], P[23 * 23];
-        const state& s = this->get_x();
-        for (int i = 0; i < 3; i++) { x[i] = s.pos[i]; x[11 + i] = s.offset_T_L_I[i]; x[14 + i] = s.vel[i]; x[17 + i] = s.bg[i]; x[20 + i] = s.ba[i]; x[23 + i] = s.grav[i]; }
-        for (int i = 0; i < 4; i++) { x[3 + i] = s.rot.coeffs()[i]; x[7 + i] = s.offset_R_L_I.coeffs()[i]; }
-        const cov& Pm = this->get_P();
-        for (int i = 0; i < 23; i++) for (int j = 0; j < 23; j++) P[i * 23 + j] = Pm(i, j);
+        pack(x, P);
         if (fl_filter_update(filter_, scan_.data(), (int)(scan_.size() / 4), x, P, R, &solve_time) != FL_OK) {
             fprintf(stderr, "esekf_b200: %s\n", fl_last_error());
             return;                                                  // state untouched, like an invalid measurement
         }
-        state out = s;
-        for (int i = 0; i < 3; i++) { out.pos[i] = x[i]; out.offset_T_L_I[i] = x[11 + i]; out.vel[i] = x[14 + i]; out.bg[i] = x[17 + i]; out.ba[i] = x[20 + i]; out.grav.vec[i] = x[23 + i]; }
-        for (int i = 0; i < 4; i++) { out.rot.coeffs()[i] = x[3 + i]; out.offset_R_L_I.coeffs()[i] = x[7 + i]; }
-        cov Pout;
-        for (int i = 0; i < 23; i++) for (int j = 0; j < 23; j++) Pout(i, j) = P[i * 23 + j];
-        this->change_x(out);
-        this->change_P(Pout);
+        unpack(x, P);
+    }
+
+    // The same update on a cloud that fl_scan_voxel_downsample left in HBM (no host hop for the points).
+    void update_from(fl_scan_t* scan, double R, double& solve_time) {
+        if (!filter_ || !scan) { fprintf(stderr, "esekf_b200::update_from: bind_map() first\n"); return; }
+        double x[26], P[23 * 23];
+        pack(x, P);
+        if (fl_filter_update_scan(filter_, scan, x, P, R, &solve_time) != FL_OK) {
+            fprintf(stderr, "esekf_b200: %s\n", fl_last_error());
+            return;
+        }
+        unpack(x, P);
+    }
+
+    // map_incremental() (laserMapping.cpp:427-474) on the device, from the state and neighbours of the last update;
+    // returns the value of ikdtree.Add_Points(PointToAdd, true) (:470) or < 0
+    int map_incremental(double filter_size_map_min, bool flg_EKF_inited) {
+        int out[3] = {0, 0, 0};
+        if (!filter_) return FL_ERR_STATE;
+        int rc = fl_filter_map_incremental(filter_, filter_size_map_min, flg_EKF_inited ? 1 : 0, out);
+        return rc == FL_OK ? out[2] : rc;
     }
 
     // Nearest_Points of the last search pass (laserMapping.cpp:102) for map_incremental (:438-460)
@@ -107,6 +118,23 @@ public:
     fl_filter_t* handle() const { return filter_; }
 
 private:
+    // state_ikfom <-> the 26-double layout of fastlio_b200.h
+    void pack(double* x, double* P) const {
+        const state& s = this->get_x();
+        for (int i = 0; i < 3; i++) { x[i] = s.pos[i]; x[11 + i] = s.offset_T_L_I[i]; x[14 + i] = s.vel[i]; x[17 + i] = s.bg[i]; x[20 + i] = s.ba[i]; x[23 + i] = s.grav[i]; }
+        for (int i = 0; i < 4; i++) { x[3 + i] = s.rot.coeffs()[i]; x[7 + i] = s.offset_R_L_I.coeffs()[i]; }
+        const cov& Pm = this->get_P();
+        for (int i = 0; i < 23; i++) for (int j = 0; j < 23; j++) P[i * 23 + j] = Pm(i, j);
+    }
+    void unpack(const double* x, const double* P) {
+        state out = this->get_x();
+        for (int i = 0; i < 3; i++) { out.pos[i] = x[i]; out.offset_T_L_I[i] = x[11 + i]; out.vel[i] = x[14 + i]; out.bg[i] = x[17 + i]; out.ba[i] = x[20 + i]; out.grav.vec[i] = x[23 + i]; }
+        for (int i = 0; i < 4; i++) { out.rot.coeffs()[i] = x[3 + i]; out.offset_R_L_I.coeffs()[i] = x[7 + i]; }
+        cov Pout;
+        for (int i = 0; i < 23; i++) for (int j = 0; j < 23; j++) Pout(i, j) = P[i * 23 + j];
+        this->change_x(out);
+        this->change_P(Pout);
+    }
     int push_params() { return filter_ ? fl_filter_set_params(filter_, max_iter_, limit_, extrinsic_est_ ? 1 : 0) : FL_OK; }
     fl_filter_t* filter_ = nullptr;
     std::vector<float> scan_;

@@ -21,5 +21,24 @@ int main() {
     kf.update_iterated_dyn_share_modified(0.001, st);
     std::vector<KD_TREE<pcl::PointXYZINormal>::PointVector> nearest;
     kf.fetch_nearest(nearest);
+    // the resident front end: raw cloud -> de-skew -> voxel grid -> update -> map_incremental, plus the local-map cube
+    fl_scan_t* scan = nullptr;
+    fl_localmap_t* cube = nullptr;
+    if (tree.handle() && fl_scan_create(&scan, tree.handle()) == FL_OK) {
+        float xyzi[4] = {1, 2, 3, 4}, t_ms[1] = {0};
+        double pose[22] = {0}, x26[26] = {0};
+        fl_scan_upload(scan, xyzi, t_ms, 1);
+        fl_scan_undistort(scan, pose, 1, x26);
+        fl_scan_voxel_downsample(scan, 0.5f);
+        kf.update_from(scan, 0.001, st);
+        kf.map_incremental(0.5, true);
+        fl_scan_destroy(scan);
+    }
+    if (fl_localmap_create(&cube, 1000.0, 100.0f) == FL_OK) {
+        double pos[3] = {0, 0, 0};
+        int deleted = 0;
+        fl_localmap_segment(cube, tree.handle(), pos, nullptr, &deleted);
+        fl_localmap_destroy(cube);
+    }
     return tree.size() + tree.validnum() + (int)nearest.size();
 }

@@ -43,7 +43,7 @@ SYMBOLS = [
     "fl_filter_create", "fl_filter_destroy", "fl_filter_set_params", "fl_filter_set_solver", "fl_filter_set_search", "fl_filter_update",
     "fl_filter_map_incremental", "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
     "fl_filter_upload_state", "fl_filter_run", "fl_filter_download_state", "fl_filter_sync",
-    "fl_filter_time_resident", "fl_filter_time_search_pass", "fl_filter_gpu_launches",
+    "fl_filter_time_resident", "fl_filter_time_search_pass", "fl_filter_time_e2e", "fl_filter_gpu_launches",
     "fl_scan_create", "fl_scan_destroy", "fl_scan_upload", "fl_scan_undistort", "fl_scan_voxel_downsample", "fl_scan_download",
     "fl_filter_update_scan", "fl_localmap_create", "fl_localmap_destroy", "fl_localmap_segment", "fl_localmap_get",
     "fl_comm_unique_id", "fl_filter_comm_init", "fl_filter_set_shard", "fl_filter_p2p_handle", "fl_filter_p2p_connect",
@@ -97,6 +97,7 @@ def load():
     L.fl_filter_time_resident.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.fl_filter_time_search_pass.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.fl_filter_gpu_launches.argtypes = [C.c_void_p]
+    L.fl_filter_time_e2e.argtypes = [C.c_void_p, _f32p, C.c_int, _f64p, _f64p, C.c_double, C.c_int, C.POINTER(C.c_double), _f64p, _f64p]
     L.fl_scan_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p]
     L.fl_scan_destroy.argtypes = [C.c_void_p]
     L.fl_scan_upload.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int]
@@ -295,6 +296,16 @@ class Esekf:
         ms = C.c_float(0.0)
         _check(self._L.fl_filter_time_search_pass(self.h, reps, int(flush_l2), C.byref(ms)))
         return ms.value
+
+    def time_e2e(self, scan4, x26, P, R: float, reps: int):
+        """Seconds for `reps` native back-to-back fl_filter_update calls with host buffers; returns (seconds, x, P)."""
+        scan4 = np.ascontiguousarray(scan4, dtype=np.float32).reshape(-1, 4)
+        x_out = np.zeros(26, dtype=np.float64)
+        P_out = np.zeros((23, 23), dtype=np.float64)
+        sec = C.c_double(0.0)
+        _check(self._L.fl_filter_time_e2e(self.h, scan4, len(scan4), np.ascontiguousarray(x26, dtype=np.float64),
+                                          np.ascontiguousarray(P, dtype=np.float64), R, reps, C.byref(sec), x_out, P_out))
+        return sec.value, x_out, P_out
 
     def gpu_launches(self) -> int:
         return _check(self._L.fl_filter_gpu_launches(self.h))

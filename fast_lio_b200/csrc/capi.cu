@@ -1,5 +1,8 @@
 // extern "C" boundary (include/fastlio_b200.h).  Thin: argument checks, handle plumbing,
 // status codes.  No torch types, no exceptions.
+#include <atomic>
+#include <chrono>
+#include <cstring>
 #include <mutex>
 #include <new>
 
@@ -12,10 +15,20 @@ const char* last_error();
 int nccl_unique_id(void* out128);
 }  // namespace fl
 
+// A map handle is shared by the filters and scan front ends created on it: they keep it alive, so destroying the
+// handles in any order is safe (fl_map_destroy only drops the caller's reference).
 struct fl_map {
     fl::Map* impl;
     std::mutex mu;
+    std::atomic<int> refs{1};
 };
+static void map_retain(fl_map* m) { m->refs.fetch_add(1, std::memory_order_relaxed); }
+static void map_release(fl_map* m) {
+    if (m->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        delete m->impl;
+        delete m;
+    }
+}
 struct fl_filter {
     fl::Filter* impl;
     fl_map* map;
@@ -71,8 +84,7 @@ int fl_map_create(fl_map_t** out, int device, float downsample_size) {
 }
 int fl_map_destroy(fl_map_t* m) {
     if (!m) return FL_OK;
-    delete m->impl;
-    delete m;
+    map_release(m);
     return FL_OK;
 }
 #define MAP_GUARD(m)                                                             \
@@ -131,6 +143,7 @@ int fl_filter_create(fl_filter_t** out, fl_map_t* map, int max_points) {
     if (!f->impl) { delete f; return FL_ERR_CAPACITY; }
     int rc = f->impl->init();
     if (rc != FL_OK) { delete f->impl; delete f; return rc; }
+    map_retain(map);
     *out = f;
     return FL_OK;
 }
@@ -138,6 +151,7 @@ int fl_filter_destroy(fl_filter_t* f) {
     if (!f) return FL_OK;
     f->flush.release();
     delete f->impl;
+    map_release(f->map);
     delete f;
     return FL_OK;
 }
@@ -211,6 +225,26 @@ int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_to
     return FL_OK;
 }
 
+// Wall time of `reps` whole fl_filter_update calls made back to back from native code -- what a C++ application
+// (the reference is one) sees per scan: host buffers in, host buffers out, every copy inside.  Each repetition starts
+// from the same prior, like the bench's resident loop.
+int fl_filter_time_e2e(fl_filter_t* f, const float* body, int nq, const double* x26, const double* P, double R, int reps,
+                       double* seconds, double* x26_out, double* P_out) {
+    if (!f || !x26 || !P || !seconds || reps < 1) return FL_ERR_ARG;
+    double x[fl::XLEN], Pw[fl::NDOF * fl::NDOF];
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; r++) {
+        memcpy(x, x26, sizeof(x));
+        memcpy(Pw, P, sizeof(Pw));
+        int rc = fl_filter_update(f, body, nq, x, Pw, R, nullptr);
+        if (rc != FL_OK) return rc;
+    }
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (x26_out) memcpy(x26_out, x, sizeof(x));
+    if (P_out) memcpy(P_out, Pw, sizeof(Pw));
+    return FL_OK;
+}
+
 // Device time of the dominant kernel alone: k_search (the kNN of the first pass of an update).
 int fl_filter_time_search_pass(fl_filter_t* f, int reps, int flush_l2, float* ms_total) {
     FILTER_GUARD(f);
@@ -260,12 +294,14 @@ int fl_scan_create(fl_scan_t** out, fl_map_t* map) {
     if (!s->impl) { delete s; return FL_ERR_CAPACITY; }
     int rc = s->impl->init();
     if (rc != FL_OK) { delete s->impl; delete s; return rc; }
+    map_retain(map);
     *out = s;
     return FL_OK;
 }
 int fl_scan_destroy(fl_scan_t* s) {
     if (!s) return FL_OK;
     delete s->impl;
+    map_release(s->map);
     delete s;
     return FL_OK;
 }

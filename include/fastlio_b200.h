@@ -56,7 +56,7 @@ int fl_version(void);
 /* KD_TREE::KD_TREE(delete_param, balance_param, box_length)          ikd_Tree.h:309, ikd_Tree.cpp:9-18
  * (the two rebuild criteria have no counterpart: leaves are re-packed by fl_map_rebuild / automatically) */
 int fl_map_create(fl_map_t** out, int device, float downsample_size);
-int fl_map_destroy(fl_map_t* m);
+int fl_map_destroy(fl_map_t* m);   /* drops the caller's reference; filters / scans created on the map keep it alive until they go */
 /* KD_TREE::set_downsample_param                                      ikd_Tree.h:319-322 */
 int fl_map_set_downsample(fl_map_t* m, float downsample_size);
 /* KD_TREE::Build(PointVector)                                        ikd_Tree.cpp:409-423 */
@@ -122,6 +122,10 @@ int fl_filter_sync(fl_filter_t* f);
 /* device time in milliseconds of `reps` back-to-back resident updates from the uploaded state
  * (CUDA events on the handle's stream); optionally flushes L2 between repetitions */
 int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_total);
+/* wall-clock seconds of `reps` consecutive fl_filter_update(body, nq, copy of x26, copy of P, R) calls issued from
+ * native code (the per-scan cost a C++ caller such as laserMapping.cpp sees); x26_out / P_out (may be NULL): last result */
+int fl_filter_time_e2e(fl_filter_t* f, const float* body_xyzi, int nq, const double* x26, const double* P, double R, int reps,
+                       double* seconds, double* x26_out, double* P_out);
 /* device time of `reps` launches of the dominant kernel alone (k_measure in search mode) */
 int fl_filter_time_search_pass(fl_filter_t* f, int reps, int flush_l2, float* ms_total);
 int fl_filter_gpu_launches(fl_filter_t* f);

@@ -69,3 +69,23 @@ def test_knn_brute_force_random():
         d = ((q[i, 0] - pts[:, 0]) ** 2 + (q[i, 1] - pts[:, 1]) ** 2) + (q[i, 2] - pts[:, 2]) ** 2   # float32, same order
         order = np.argsort(d, kind="stable")[:5]
         assert np.array_equal(gd[i], d[order])
+
+
+def test_handles_may_be_destroyed_in_any_order(problems):
+    """The C ABI keeps a map alive while a filter or a scan front end created on it exists (Python's cyclic GC may
+    finalise the wrappers in any order; a C++ caller's static destructors may too)."""
+    import ctypes as C
+    pr = problems("tiny")
+    L = api.load()
+    m, f, s = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert L.fl_map_create(C.byref(m), 0, 0.5) == 0
+    assert L.fl_map_build(m, pr.map_pts, len(pr.map_pts)) == 0
+    assert L.fl_filter_create(C.byref(f), m, 1000) == 0
+    assert L.fl_scan_create(C.byref(s), m) == 0
+    assert L.fl_map_destroy(m) == 0                      # the caller lets go first
+    x = pr.x_prior.copy(); P = pr.P_prior.copy()
+    assert L.fl_filter_update(f, pr.scan, len(pr.scan), x, P, pr.R, None) == 0      # the filter still has its map
+    assert L.fl_filter_destroy(f) == 0
+    assert L.fl_scan_destroy(s) == 0
+    t = api.KdTree(0, 0.5); t.Build(pr.map_pts)           # and nothing is left pending in the CUDA error state
+    assert t.validnum() == len(pr.map_pts)

@@ -24,7 +24,7 @@ def chain():
     n = s.voxel_downsample(0.5)
     x, P, _ = s.update(f, pr.x_prior, pr.P_prior, pr.R)
     return n, x
-for _ in range(10):
+for _ in range(min(10, reps)):
     n_down, x_gpu = chain()
 stages = {}
 def timed(name, fn):
@@ -33,14 +33,17 @@ t_all = time.perf_counter()
 for _ in range(reps):
     n_down, x_gpu = chain()
 t_all = (time.perf_counter() - t_all) / reps
-for _ in range(reps // 4):                                    # same chain with a sync after each stage, for the breakdown
+for _ in range(max(1, reps // 4)):                                    # same chain with a sync after each stage, for the breakdown
     timed("upload", lambda: s.upload(raw.xyzi, raw.offset_ms))
     timed("undistort", lambda: s.undistort(raw.imu_pose, raw.x_end))
     timed("voxelgrid", lambda: s.voxel_downsample(0.5))
     timed("update", lambda: s.update(f, pr.x_prior, pr.P_prior, pr.R))
 gpu = {"ms_per_scan": 1e3 * t_all, "scans_per_s": 1.0 / t_all, "n_down": int(n_down),
-       "stage_ms_synced": {k: 1e3 * v / (reps // 4) for k, v in stages.items()}}
+       "stage_ms_synced": {k: 1e3 * v / max(1, reps // 4) for k, v in stages.items()}}
 
+if cpu_reps < 2:                                                # GPU side only (profiling runs)
+    print(json.dumps({"workload": f"raw {n_raw} pts", "gpu": gpu}))
+    sys.exit(0)
 t = bind.KdTree(pr.map_pts, "auto")
 c = {}
 x_cpu = None

@@ -60,6 +60,10 @@ struct KBest {
     }
 };
 
+// Squared distances are non-negative floats, so their bit patterns order like the values and
+// +inf (0x7f800000) can serve as the "no candidate" marker of the integer warp reductions.
+constexpr unsigned INF_BITS = 0x7f800000u;
+
 // Visit one leaf bucket (and its overflow chain): each lane scores one slot, then the
 // (at most K) improving candidates are extracted in ascending order.
 __device__ __forceinline__ void knn_leaf(const MapView& m, int leaf, float qx, float qy, float qz,
@@ -67,18 +71,17 @@ __device__ __forceinline__ void knn_leaf(const MapView& m, int leaf, float qx, f
     while (leaf >= 0) {
         const float4 p = __ldg(&m.pts[leaf * LEAF + lane]);
         const int nxt = __ldg(&m.next[leaf]);
-        float d = slot_valid(p) ? sq_dist3(qx, qy, qz, p.x, p.y, p.z) : INFINITY;
+        unsigned key = slot_valid(p) ? __float_as_uint(sq_dist3(qx, qy, qz, p.x, p.y, p.z)) : INF_BITS;
         if (kb.n == 0) {
             // empty list (the first leaf of a query): the r-th smallest goes straight to lane r -- no merge
-            unsigned best = 0xffffffffu;
-#pragma unroll 1
+            unsigned best = INF_BITS;
+#pragma unroll
             for (int r = 0; r < KNN_K; r++) {
-                const unsigned key = (d < INFINITY) ? __float_as_uint(d) : 0xffffffffu;
                 best = __reduce_min_sync(FULL, key);
-                if (best == 0xffffffffu) break;
+                if (best == INF_BITS) break;
                 const int src = __ffs(__ballot_sync(FULL, key == best)) - 1;
                 if (lane == r) { kb.d = __uint_as_float(best); kb.idx = leaf * LEAF + src; }
-                if (lane == src) d = INFINITY;
+                if (lane == src) key = INF_BITS;
                 kb.n = r + 1;
             }
             if (kb.n == KNN_K) kb.w = __uint_as_float(best);
@@ -87,12 +90,11 @@ __device__ __forceinline__ void knn_leaf(const MapView& m, int leaf, float qx, f
         }
 #pragma unroll 1
         for (int it = 0; it < KNN_K; it++) {
-            const unsigned key = (d < kb.w) ? __float_as_uint(d) : 0xffffffffu;   // d >= 0: bits order like floats
             const unsigned best = __reduce_min_sync(FULL, key);
-            if (best == 0xffffffffu) break;
+            if (best >= __float_as_uint(kb.w)) break;       // nothing strictly closer than the k-th best is left (covers the marker)
             const int src = __ffs(__ballot_sync(FULL, key == best)) - 1;
             kb.insert(__uint_as_float(best), leaf * LEAF + src, lane);
-            if (lane == src) d = INFINITY;
+            if (lane == src) key = INF_BITS;
         }
         leaf = nxt;
     }
@@ -100,25 +102,26 @@ __device__ __forceinline__ void knn_leaf(const MapView& m, int leaf, float qx, f
 
 // Visit node `node` of level L (its children are entities of level L-1).  Children are
 // taken nearest-first and re-tested against the shrinking k-th best distance after each
-// return -- the pruning rule of KD_TREE::Search (ikd_Tree.cpp:1097-1243).
+// return -- the pruning rule of KD_TREE::Search (ikd_Tree.cpp:1097-1243).  The ordering key is
+// the box distance with its low 5 mantissa bits traded for the lane id; a child is skipped only
+// when even that rounded-DOWN distance is not below the k-th best, so pruning never drops a
+// child that could matter (it may visit one whose distance ties the bound within 2^-18).
 template <int L>
 __device__ __forceinline__ void knn_node(const MapView& m, int node, float qx, float qy, float qz,
                                          KBest& kb, int lane) {
     const int e = node * FAN + lane;
-    float di = INFINITY;
+    unsigned key = 0xffffffffu;
     if (e < m.count[L - 1]) {
         const float4 lo = __ldg(&m.ebox[L - 1][2 * e]);
         const float4 hi = __ldg(&m.ebox[L - 1][2 * e + 1]);
-        di = box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+        key = (__float_as_uint(box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) & ~31u) | (unsigned)lane;
     }
 #pragma unroll 1
     while (true) {
-        // order by distance (low 5 mantissa bits traded for the lane id; pruning stays exact)
-        const unsigned key = (di < kb.w) ? ((__float_as_uint(di) & ~31u) | (unsigned)lane) : 0xffffffffu;
         const unsigned best = __reduce_min_sync(FULL, key);
-        if (best == 0xffffffffu) break;
+        if ((best & ~31u) >= __float_as_uint(kb.w)) break;
         const int c = best & 31;
-        if (lane == c) di = INFINITY;
+        if (lane == c) key = 0xffffffffu;
         if constexpr (L == 1) knn_leaf(m, node * FAN + c, qx, qy, qz, kb, lane);
         else knn_node<L - 1>(m, node * FAN + c, qx, qy, qz, kb, lane);
     }
@@ -131,23 +134,21 @@ constexpr int ROOT_FAN = 64;
 template <int L>
 __device__ __forceinline__ void knn_root(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
     const int cnt = m.count[L - 1];
-    float d0 = INFINITY, d1 = INFINITY;
+    unsigned k0 = 0xffffffffu, k1 = 0xffffffffu;
     if (lane < cnt) {
         const float4 lo = __ldg(&m.ebox[L - 1][2 * lane]), hi = __ldg(&m.ebox[L - 1][2 * lane + 1]);
-        d0 = box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+        k0 = (__float_as_uint(box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) & ~63u) | (unsigned)lane;
     }
     if (lane + 32 < cnt) {
         const float4 lo = __ldg(&m.ebox[L - 1][2 * (lane + 32)]), hi = __ldg(&m.ebox[L - 1][2 * (lane + 32) + 1]);
-        d1 = box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+        k1 = (__float_as_uint(box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) & ~63u) | (unsigned)(lane + 32);
     }
 #pragma unroll 1
     while (true) {
-        const unsigned k0 = (d0 < kb.w) ? ((__float_as_uint(d0) & ~63u) | (unsigned)lane) : 0xffffffffu;
-        const unsigned k1 = (d1 < kb.w) ? ((__float_as_uint(d1) & ~63u) | (unsigned)(lane + 32)) : 0xffffffffu;
         const unsigned best = __reduce_min_sync(FULL, min(k0, k1));
-        if (best == 0xffffffffu) break;
+        if ((best & ~63u) >= __float_as_uint(kb.w)) break;
         const int c = best & 63;
-        if (lane == (c & 31)) { if (c < 32) d0 = INFINITY; else d1 = INFINITY; }
+        if (lane == (c & 31)) { if (c < 32) k0 = 0xffffffffu; else k1 = 0xffffffffu; }
         if constexpr (L == 1) knn_leaf(m, c, qx, qy, qz, kb, lane);
         else knn_node<L - 1>(m, c, qx, qy, qz, kb, lane);
     }

@@ -191,6 +191,7 @@ int fl_filter_debug_prof(fl_filter_t* f, long long* out16) {
     FILTER_GUARD(f);
     if (!out16) return FL_ERR_ARG;
     FL_CUDA(cudaMemcpy(out16, f->impl->ctl_device()->prof, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; i++) out16[12 + i] = f->impl->host_ns()[i];       // host-side ns of the last fl_filter_update
     return FL_OK;
 }
 int fl_filter_gpu_launches(fl_filter_t* f) { FILTER_GUARD(f); return f->impl->gpu_launches(); }

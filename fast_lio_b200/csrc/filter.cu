@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 
 #include <cub/device/device_select.cuh>
@@ -807,6 +808,8 @@ __global__ void __launch_bounds__(SEARCH_T_THREADS) k_search_t(MapView m, ScanVi
 //   mode 0: finishes the Kalman step of this pass on the spot (single GPU -- no extra launch),
 //   mode 1: publishes the 92 sums for the all-reduce across ranks (k_solve_only follows).
 // Waiting cannot deadlock: block 0 holds no resource another block needs in order to run.
+__device__ __forceinline__ void mirror_result(const FilterCtl* ctl);
+
 template <bool EXTR, int SOLVER>
 __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterCtl* ctl, double* __restrict__ partials,
                                                              double* red_g, int mode, PassLog* logs, P2PState* p2p) {
@@ -918,6 +921,20 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
         __syncthreads();
     }
     solve_finish<SOLVER, EXTR>(S, ctl, sc, logs);
+    mirror_result(ctl);
+}
+
+// The pass that ends the update stores the result (header, state, covariance) straight into the caller-visible
+// page-locked mirror over PCIe: the host then only waits for the stream instead of queueing a device-to-host copy
+// behind the last kernel.  Block-wide; the block's own writes to ctl are visible after the barrier.
+__device__ __forceinline__ void mirror_result(const FilterCtl* ctl) {
+    __syncthreads();
+    if (!ctl->done || !ctl->host_mirror) return;
+    constexpr int ND = (int)(offsetof(FilterCtl, P_prop) / sizeof(double));
+    static_assert(offsetof(FilterCtl, P_prop) % sizeof(double) == 0, "mirror copies 8-byte words");
+    const double* src = reinterpret_cast<const double*>(ctl);
+    double* dst = reinterpret_cast<double*>(ctl->host_mirror);
+    for (int i = threadIdx.x; i < ND; i += blockDim.x) dst[i] = src[i];
 }
 
 // multi-GPU: the Kalman step from the all-reduced sums
@@ -932,6 +949,7 @@ __global__ void __launch_bounds__(RESID_THREADS) k_solve_only(FilterCtl* ctl, co
     if (threadIdx.x < NRED) S.red[threadIdx.x] = red_g[threadIdx.x];
     __syncthreads();
     solve_finish<SOLVER, EXTR>(S, ctl, sc, logs);
+    mirror_result(ctl);
 }
 #undef STAMP
 
@@ -1030,7 +1048,8 @@ Filter::~Filter() {
 
 int Filter::init() {
     FL_CUDA(cudaSetDevice(map_->device()));
-    if (const char* e = getenv("FASTLIO_B200_NO_PDL")) pdl_ = !(e[0] == '1');      // A/B switch for tuning
+    if (const char* e = getenv("FASTLIO_B200_NO_PDL")) pdl_ = !(e[0] == '1');      // A/B switches for tuning
+    if (const char* e = getenv("FASTLIO_B200_NO_MIRROR")) mirror_ = !(e[0] == '1');
     FL_CHECK(ctl_.reserve(sizeof(FilterCtl)));
     FL_CHECK(ctl0_.reserve(sizeof(FilterCtl)));
     FL_CHECK(red_.reserve(sizeof(double) * PSTRIDE));
@@ -1108,6 +1127,7 @@ int Filter::upload_state(const double* x26, const double* P, double R, bool snap
     FilterCtl& c = *h_ctl_;
     c.iter = -1; c.t = 0; c.converge = 1; c.done = 0; c.n_pass = 0; c.error = 0; c.ticket = 0; c.pad_ = 0;
     c.max_iter = max_iter_;
+    c.host_mirror = mirror_ ? h_ctl_ : nullptr;
     c.extrinsic_est = extrinsic_est_;
     c.R = R;
     for (int i = 0; i < NDOF; i++) c.limit[i] = limit_[i];
@@ -1205,8 +1225,11 @@ int Filter::sync() {
 
 int Filter::download_state(double* x26, double* P, int* n_pass) {
     FL_CUDA(cudaSetDevice(map_->device()));
-    FL_CUDA(cudaMemcpyAsync(h_ctl_, ctl_.ptr, offsetof(FilterCtl, P_prop), cudaMemcpyDeviceToHost, stream()));
     FL_CUDA(cudaStreamSynchronize(stream()));
+    if (!(mirror_ && h_ctl_->done)) {                   // nothing ran since the upload (or the mirror is off): fetch the block
+        FL_CUDA(cudaMemcpyAsync(h_ctl_, ctl_.ptr, offsetof(FilterCtl, P_prop), cudaMemcpyDeviceToHost, stream()));
+        FL_CUDA(cudaStreamSynchronize(stream()));
+    }
     if (h_ctl_->error) { set_last_error("update: singular system on device"); return FL_ERR_STATE; }
     if (x26) memcpy(x26, h_ctl_->x, sizeof(double) * XLEN);
     if (P) memcpy(P, h_ctl_->P, sizeof(double) * NDOF * NDOF);
@@ -1226,12 +1249,22 @@ int Filter::update_any(const float* body_xyzi, const float4* d_body, int nq, dou
     FL_CUDA(cudaSetDevice(map_->device()));
     if (solve_time_s && !ev0_) { FL_CUDA(cudaEventCreate(&ev0_)); FL_CUDA(cudaEventCreate(&ev1_)); }
     if (solve_time_s) FL_CUDA(cudaEventRecord(ev0_, stream()));
+    const auto h0 = std::chrono::steady_clock::now();
     if (d_body) FL_CHECK(set_scan_device(d_body, nq));
     else FL_CHECK(upload_scan(body_xyzi, nq));
     FL_CHECK(upload_state(x26, P, R, false));
+    const auto h1 = std::chrono::steady_clock::now();
     FL_CHECK(run_passes());
     if (solve_time_s) FL_CUDA(cudaEventRecord(ev1_, stream()));
+    const auto h2 = std::chrono::steady_clock::now();
     FL_CHECK(download_state(x26, P, nullptr));
+    const auto h3 = std::chrono::steady_clock::now();
+    // host-side anatomy of the last call (tuning aid, fl_filter_debug_prof slots 12..15): ns spent enqueueing the uploads,
+    // enqueueing the passes, and waiting for the result
+    host_ns_[0] = std::chrono::duration_cast<std::chrono::nanoseconds>(h1 - h0).count();
+    host_ns_[1] = std::chrono::duration_cast<std::chrono::nanoseconds>(h2 - h1).count();
+    host_ns_[2] = std::chrono::duration_cast<std::chrono::nanoseconds>(h3 - h2).count();
+    host_ns_[3] = std::chrono::duration_cast<std::chrono::nanoseconds>(h3 - h0).count();
     if (solve_time_s) {
         float ms = 0.f;
         FL_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
@@ -1298,8 +1331,11 @@ int Filter::get_selected(unsigned char* out, int nq) {
 }
 int Filter::get_pass_logs(PassLog* out, int cap, int* n) {
     FL_CUDA(cudaSetDevice(map_->device()));
-    FL_CUDA(cudaMemcpyAsync(h_ctl_, ctl_.ptr, offsetof(FilterCtl, P_prop), cudaMemcpyDeviceToHost, stream()));
     FL_CUDA(cudaStreamSynchronize(stream()));
+    if (!(mirror_ && h_ctl_->done)) {                   // nothing ran since the upload (or the mirror is off): fetch the block
+        FL_CUDA(cudaMemcpyAsync(h_ctl_, ctl_.ptr, offsetof(FilterCtl, P_prop), cudaMemcpyDeviceToHost, stream()));
+        FL_CUDA(cudaStreamSynchronize(stream()));
+    }
     const int np = std::min(std::min(h_ctl_->n_pass, MAX_LOGS), cap);
     if (np > 0) {
         FL_CUDA(cudaMemcpyAsync(out, logs_.ptr, sizeof(PassLog) * (size_t)np, cudaMemcpyDeviceToHost, stream()));

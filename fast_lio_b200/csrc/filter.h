@@ -37,6 +37,7 @@ struct FilterCtl {
     double P[NDOF * NDOF];
     double P_prop[NDOF * NDOF];
     long long prof[16];  // clock64() stamps of the last solve_pass (thread 0), for tuning
+    FilterCtl* host_mirror;  // page-locked, device-mapped copy on the host: the pass that ends the update stores the result there
 };
 
 struct ScanView {
@@ -102,6 +103,7 @@ public:
     int p2p_connect(int nranks, int rank, const void* handles64);
 
     int gpu_launches() const { return launches_; }
+    const long long* host_ns() const { return host_ns_; }
     const float4* nearest_device() const { return scan_.nearest; }
     const ScanView& scan() const { return scan_; }
     cudaStream_t stream() const { return map_->stream(); }
@@ -117,6 +119,7 @@ private:
     double limit_[NDOF];
     int extrinsic_est_ = 0;
     int solver_ = 1;
+    bool mirror_ = true;               // the last pass stores the result into the page-locked host block itself
     bool pdl_ = true;                  // programmatic dependent launch between the kernels of a scan
     int search_mode_ = 0;              // 0: one warp per query (k_search, default); 1: one thread per query (k_search_t, measured 2.8x slower)
     ScanView scan_;
@@ -126,6 +129,7 @@ private:
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int sms_ = 0, search_grid_max_ = 0, max_resid_grid_ = 0, resid_grid_ = 1;
     int launches_ = 0;
+    long long host_ns_[4] = {0, 0, 0, 0};
     bool shard_set_ = false;
     // NCCL (resolved lazily with dlopen so that single-GPU use needs no NCCL at all)
     NcclApi* nccl_ = nullptr;

@@ -318,7 +318,8 @@ __device__ __forceinline__ void warp_accumulate(bool contrib, const double* h, d
 // world frame thread-parallel (FP64, laserMapping.cpp:656-661), then the warp walks the map once
 // per point.  Runs only when the filter asks for a search (ekfom_data.converge, decided on the
 // device); few registers, so that many warps hide the latency of the dependent tree loads.
-__global__ void __launch_bounds__(SEARCH_THREADS) k_search(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
+template <int MINB>
+__global__ void __launch_bounds__(SEARCH_THREADS, MINB) k_search(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
     pdl_wait();                 // the previous pass's Kalman step (or the upload) is complete and visible
     pdl_launch();               // k_residual may start: its solver block prepares while we search
     if (ctl->done || !ctl->converge) return;
@@ -326,9 +327,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS) k_search(MapView m, ScanView s
     const int gwarp = (blockIdx.x * SEARCH_THREADS + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * SEARCH_THREADS) >> 5;
     const int q0 = sc.q_begin, q1 = sc.q_end;
-    const int per_warp = (q1 - q0 + nwarps - 1) / nwarps;
-    const int wq0 = q0 + gwarp * per_warp;
-    const int wq1 = min(q1, wq0 + per_warp);
+    // balanced split: every warp gets floor or ceil of (points / warps) -- with a ceil-sized run per warp the last
+    // ~10 % of the warps (whole SMs' worth) would sit idle while the others carry their points
+    const long long nq = q1 - q0;
+    const int wq0 = q0 + (int)(nq * gwarp / nwarps);
+    const int wq1 = q0 + (int)(nq * (gwarp + 1) / nwarps);
     for (int base = wq0; base < wq1; base += 32) {
         const int myq = base + lane;
         float wx = 0.f, wy = 0.f, wz = 0.f;
@@ -1063,7 +1066,10 @@ int Filter::init() {
     // k_residual: one thread per point, at most max_resid_grid_ blocks (one partial row each)
     int dev = map_->device(), occ = 0;
     FL_CUDA(cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, dev));
-    FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search, SEARCH_THREADS, 0));
+    if (const char* e = getenv("FASTLIO_B200_SEARCH_OCC")) search_occ_ = atoi(e);      // A/B: 4 (62 regs), 5 (<= 51) or 6 (<= 42) blocks per SM
+    if (search_occ_ == 6) FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<6>, SEARCH_THREADS, 0));
+    else if (search_occ_ == 5) FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<5>, SEARCH_THREADS, 0));
+    else FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<4>, SEARCH_THREADS, 0));
     search_grid_max_ = sms_ * std::max(1, occ);
     max_resid_grid_ = sms_;
     FL_CHECK(partials_.reserve(sizeof(double) * PSTRIDE * (size_t)max_resid_grid_));
@@ -1127,7 +1133,7 @@ int Filter::upload_state(const double* x26, const double* P, double R, bool snap
     FilterCtl& c = *h_ctl_;
     c.iter = -1; c.t = 0; c.converge = 1; c.done = 0; c.n_pass = 0; c.error = 0; c.ticket = 0; c.pad_ = 0;
     c.max_iter = max_iter_;
-    c.host_mirror = mirror_ ? h_ctl_ : nullptr;
+    c.host_mirror = (mirror_ && !snapshot) ? h_ctl_ : nullptr;      // whole-update calls only: resident pipelines fetch the result when they want it
     c.extrinsic_est = extrinsic_est_;
     c.R = R;
     for (int i = 0; i < NDOF; i++) c.limit[i] = limit_[i];
@@ -1190,7 +1196,10 @@ int Filter::launch_search_only() {
         return FL_OK;
     }
     const int sgrid = std::max(1, std::min(search_grid_max_, (nq * 32 + SEARCH_THREADS - 1) / SEARCH_THREADS));
-    FL_CUDA(launch_pdl(k_search, sgrid, SEARCH_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
+    const FilterCtl* cc = ctl_.as<FilterCtl>();
+    if (search_occ_ == 6) FL_CUDA(launch_pdl(k_search<6>, sgrid, SEARCH_THREADS, stream(), pdl_, map_->view(), scan_, cc));
+    else if (search_occ_ == 5) FL_CUDA(launch_pdl(k_search<5>, sgrid, SEARCH_THREADS, stream(), pdl_, map_->view(), scan_, cc));
+    else FL_CUDA(launch_pdl(k_search<4>, sgrid, SEARCH_THREADS, stream(), pdl_, map_->view(), scan_, cc));
     return FL_OK;
 }
 int Filter::launch_residual_only() {

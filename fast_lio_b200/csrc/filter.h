@@ -121,6 +121,7 @@ private:
     int solver_ = 1;
     bool mirror_ = true;               // the last pass stores the result into the page-locked host block itself
     bool pdl_ = true;                  // programmatic dependent launch between the kernels of a scan
+    int search_occ_ = 5;               // resident k_search blocks per SM the kernel is compiled for
     int search_mode_ = 0;              // 0: one warp per query (k_search, default); 1: one thread per query (k_search_t, measured 2.8x slower)
     ScanView scan_;
     DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, plane_, partials_, red_, ctl_, ctl0_, logs_;

@@ -121,9 +121,20 @@ __global__ void k_vg_minmax(const float4* __restrict__ pts, int n, VgCtl* c) {
             mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
         }
     }
-    if ((threadIdx.x & 31) == 0) {
+    // one set of atomics per BLOCK: all of them hit the same six words, so every atomic that is saved is latency saved
+    __shared__ float s_mn[8][3], s_mx[8][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
 #pragma unroll
-        for (int a = 0; a < 3; a++) { atomic_min_float(&c->mn[a], mn[a]); atomic_max_float(&c->mx[a], mx[a]); }
+        for (int a = 0; a < 3; a++) { s_mn[warp][a] = mn[a]; s_mx[warp][a] = mx[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int a = threadIdx.x;
+        float lo = s_mn[0][a], hi = s_mx[0][a];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) { lo = fminf(lo, s_mn[w][a]); hi = fmaxf(hi, s_mx[w][a]); }
+        atomic_min_float(&c->mn[a], lo);
+        atomic_max_float(&c->mx[a], hi);
     }
 }
 
@@ -270,7 +281,7 @@ int ScanFrontEnd::voxel_downsample(float leaf, int* n_out) {
     VgCtl* ctl = ctl_.as<VgCtl>();
     const int block = 256, grid = (n + block - 1) / block;
     k_vg_reset<<<1, 32, 0, st>>>(ctl);
-    k_vg_minmax<<<std::min(grid, 148 * 4), block, 0, st>>>(raw_.as<float4>(), n, ctl);
+    k_vg_minmax<<<std::min(grid, 148), block, 0, st>>>(raw_.as<float4>(), n, ctl);
     k_vg_keys<<<grid, block, 0, st>>>(raw_.as<float4>(), n, leaf, ctl, keys_.as<unsigned>(), vals_.as<int>());
     size_t tmp_sort = 0, tmp_scan = 0;
     FL_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys_.as<unsigned>(), keys_alt_.as<unsigned>(), vals_.as<int>(), vals_alt_.as<int>(), n, 0, 32, st));

@@ -20,4 +20,11 @@ for i in range(n + 20):
 print("us per call: enqueue uploads %.1f, enqueue passes %.1f, wait %.1f, total %.1f" % tuple(acc / n / 1e3))
 sec, _, _ = f.time_e2e(pr.scan, pr.x_prior, pr.P_prior, pr.R, 1000)
 print("back-to-back native: %.1f us/scan" % (sec / 1000 * 1e6))
+sts = []
+for i in range(220):
+    x, P, st = f.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
+    if i >= 20:
+        sts.append(st)
+print("device time (events around uploads + passes): median %.1f us" % (1e6 * float(np.median(sts))))
+f.upload_scan(pr.scan); f.upload_state(pr.x_prior, pr.P_prior, pr.R)
 print("resident warm: %.1f us/scan, flushed: %.1f" % (1e3 * f.time_resident(500, False) / 500, 1e3 * f.time_resident(500, True) / 500))

@@ -211,6 +211,7 @@ int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_to
     for (int r = 0; r < reps; r++) {
         FL_CHECK(F->restore_state());
         if (flush_l2) FL_CUDA(cudaMemsetAsync(f->flush.ptr, r & 0xff, flush_bytes, st));
+        FL_CHECK(F->p2p_barrier());           // multi-GPU: all ranks enter the timed step together (no-op on one GPU)
         FL_CUDA(cudaEventRecord(e0, st));
         int rc = F->run_passes();
         if (rc != FL_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }

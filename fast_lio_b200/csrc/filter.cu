@@ -956,6 +956,27 @@ __global__ void __launch_bounds__(RESID_THREADS) k_solve_only(FilterCtl* ctl, co
 }
 #undef STAMP
 
+// Device-side rendezvous over the peer mailboxes: every rank raises its slot in every peer's barrier array and waits
+// for all slots of its own.  Used by the benchmark to start a timed step on all ranks together (the first exchange
+// of a pass would otherwise absorb -- and bill -- whatever skew the untimed L2 flush and the host loops left).
+__global__ void k_p2p_barrier(P2PState* p2p) {
+    const int nr = p2p->nranks, me = p2p->rank;
+    const unsigned long long epoch = p2p->bar_epoch + 1;
+    if ((int)threadIdx.x < nr) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p2p->peer_bar[threadIdx.x] + me), "l"(epoch) : "memory");
+        const unsigned long long* mine = p2p->peer_bar[me] + threadIdx.x;
+        unsigned long long seen = 0;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+            if (seen >= epoch) break;
+            __nanosleep(32);
+        } while (clock64() - t0 < 4000000000ll);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) p2p->bar_epoch = epoch;
+}
+
 // ============================================================================= map_incremental
 // laserMapping.cpp:427-474: which scan points enter the map, and how.  One thread per point.
 __global__ void k_map_incremental(ScanView sc, const FilterCtl* __restrict__ ctl, double fsm, int ekf_inited,
@@ -1356,7 +1377,7 @@ int Filter::get_pass_logs(PassLog* out, int cap, int* n) {
 
 int Filter::p2p_local_handle(void* out64) {
     FL_CUDA(cudaSetDevice(map_->device()));
-    const size_t bytes = sizeof(double) * 2 * P2P_MAX_RANKS * PSTRIDE + sizeof(unsigned long long) * P2P_MAX_RANKS;
+    const size_t bytes = sizeof(double) * 2 * P2P_MAX_RANKS * PSTRIDE + sizeof(unsigned long long) * 2 * P2P_MAX_RANKS;   // mail, flags, barrier slots
     if (!mailbox_.ptr) {
         FL_CHECK(mailbox_.reserve(bytes));
         FL_CUDA(cudaMemset(mailbox_.ptr, 0, mailbox_.bytes));
@@ -1385,12 +1406,21 @@ int Filter::p2p_connect(int nranks, int rank, const void* handles64) {
         }
         st.peer_mail[r] = (double*)base;
         st.peer_flag[r] = (unsigned long long*)((char*)base + sizeof(double) * 2 * P2P_MAX_RANKS * PSTRIDE);
+        st.peer_bar[r] = st.peer_flag[r] + P2P_MAX_RANKS;
     }
     // NOTE the mailbox stride uses P2P_MAX_RANKS rows per parity only for the allocation size; rows are indexed [par * nranks + r]
     FL_CHECK(p2p_.reserve(sizeof(P2PState)));
     FL_CUDA(cudaMemcpy(p2p_.ptr, &st, sizeof(st), cudaMemcpyHostToDevice));
     nranks_ = nranks; rank_ = rank;
     p2p_on_ = nranks > 1;
+    return FL_OK;
+}
+
+int Filter::p2p_barrier() {
+    if (!p2p_on_) return FL_OK;
+    FL_CUDA(cudaSetDevice(map_->device()));
+    k_p2p_barrier<<<1, 32, 0, stream()>>>(p2p_.as<P2PState>());
+    FL_CUDA(cudaGetLastError());
     return FL_OK;
 }
 

@@ -59,7 +59,9 @@ constexpr int P2P_MAX_RANKS = 8;
 struct P2PState {
     double* peer_mail[P2P_MAX_RANKS];                 // mailbox of rank r (mapped through CUDA IPC)
     unsigned long long* peer_flag[P2P_MAX_RANKS];     // its flag array
+    unsigned long long* peer_bar[P2P_MAX_RANKS];      // rank r's barrier slots (k_p2p_barrier: aligns the ranks before a timed step)
     unsigned long long epoch;                         // passes exchanged so far (identical on all ranks)
+    unsigned long long bar_epoch;                     // barriers passed so far
     int nranks, rank;
 };
 
@@ -101,6 +103,7 @@ public:
     // fused all-reduce over NVLink peer memory instead of NCCL (one kernel per pass)
     int p2p_local_handle(void* out64);
     int p2p_connect(int nranks, int rank, const void* handles64);
+    int p2p_barrier();                                 // device-side rendezvous of all ranks on the stream (no-op on one rank)
 
     int gpu_launches() const { return launches_; }
     const long long* host_ns() const { return host_ns_; }

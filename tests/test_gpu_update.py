@@ -172,3 +172,41 @@ def test_thread_per_query_search_gives_identical_update(problems):
     for k in (1,):
         assert np.array_equal(out[0][3], out[k][3]) and np.array_equal(out[0][2], out[k][2])
         assert np.array_equal(out[0][0], out[k][0]) and np.array_equal(out[0][1], out[k][1])
+
+
+@pytest.mark.parametrize("n_pts", [0, 1, 4])
+def test_empty_and_tiny_scans(problems, n_pts):
+    """laserMapping.cpp:930-934 skips scans with < 5 points before the update is ever called; called anyway, the update must
+    behave like the reference's: an empty or tiny scan contributes few or no rows, the passes run, nothing crashes."""
+    pr = problems("tiny")
+    scan = pr.scan[:n_pts].copy()
+    ref_tree = bind.KdTree(pr.map_pts, "auto")
+    o = bind.update_iterated(ref_tree, scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, 0)
+    t = api.KdTree(0, 0.5); t.Build(pr.map_pts)
+    f = api.Esekf(t, max_points=64, max_iter=pr.cfg.max_iter)
+    x, P, _ = f.update_iterated_dyn_share_modified(scan, pr.x_prior, pr.P_prior, pr.R)
+    logs = f.pass_logs()
+    assert len(logs) == len(o.passes)
+    assert [l["effct"] for l in logs] == [p["effct"] for p in o.passes]
+    check_state(o, x, P)
+    if n_pts == 0:
+        assert np.array_equal(x, pr.x_prior)
+
+
+def test_update_against_a_map_with_fewer_than_k_points(problems):
+    """Nearest_Search returns < 5 neighbours: point_selected_surf stays false for every point (laserMapping.cpp:671)."""
+    pr = problems("tiny")
+    few = pr.map_pts[:3].copy()
+    t = api.KdTree(0, 0.5); t.Build(few)
+    f = api.Esekf(t, max_points=len(pr.scan), max_iter=pr.cfg.max_iter)
+    x, P, _ = f.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
+    assert np.array_equal(x, pr.x_prior)
+    logs = f.pass_logs()
+    assert all(l["effct"] == 0 for l in logs)
+    near, cnt = f.nearest(len(pr.scan))
+    assert (cnt == 3).all() and not f.selected(len(pr.scan)).any()
+    e = api.KdTree(0, 0.5); e.Build(np.zeros((0, 4), np.float32))      # and against an empty map
+    g = api.Esekf(e, max_points=len(pr.scan), max_iter=pr.cfg.max_iter)
+    x, P, _ = g.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
+    assert np.array_equal(x, pr.x_prior)
+    assert (g.nearest(len(pr.scan))[1] == 0).all()

@@ -24,6 +24,8 @@
 namespace fl {
 
 constexpr int PSTRIDE = 96;          // doubles per partial row (NRED = 92 padded)
+// peer mailbox: [2 parities][P2P_MAX_RANKS slots][PSTRIDE values] x two tagged 8-byte words per value
+constexpr size_t P2P_MAIL_BYTES = sizeof(unsigned long long) * 2 * 2 * P2P_MAX_RANKS * PSTRIDE;
 constexpr int SEARCH_THREADS = 256;
 constexpr int SEARCH_T_THREADS = 128;
 constexpr int RESID_THREADS = 256;
@@ -890,35 +892,41 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
     }
     if (mode == 1) return;
     if (mode == 2) {
-        // ---- all-reduce over peer memory, fused: publish my 92 sums into every rank's mailbox, raise my
-        // epoch flag there, wait for everybody's flag here, add the rows in rank order (bit-identical on all ranks)
+        // ---- all-reduce over peer memory, fused.  Low-latency protocol: every 8-byte word that crosses NVLink carries
+        // half a double and the 32-bit epoch, so the data IS the flag -- no fence, no separate flag round trip.  Each rank
+        // stores its 92 sums into its slot of every rank's mailbox (its own included) and then reads the slots of its own
+        // mailbox in rank order, spinning on a word until it shows this epoch: every rank adds the same numbers in the
+        // same order and ends with the bit-identical sum.  Two parities: a rank can be at most one exchange ahead.
         const int nr = p2p->nranks, me = p2p->rank;
         const unsigned long long epoch = p2p->epoch + 1;
+        const unsigned long long tag = (epoch & 0xffffffffull) << 32;
         const int par = (int)(epoch & 1ull);
-        for (int r = warp; r < nr; r += NW) {
-            double* dst = p2p->peer_mail[r] + ((size_t)par * nr + me) * PSTRIDE;
-            for (int o = lane; o < PSTRIDE; o += 32) dst[o] = S.red[o];
+        for (int idx = threadIdx.x; idx < nr * PSTRIDE; idx += RESID_THREADS) {
+            const int r = idx / PSTRIDE, o = idx - r * PSTRIDE;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(S.red[o]);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(p2p->peer_mail[r]) + (((size_t)par * nr + me) * PSTRIDE + o) * 2;
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(tag | (bits & 0xffffffffull)) : "memory");
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(tag | (bits >> 32)) : "memory");
         }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < nr) {
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p2p->peer_flag[threadIdx.x] + me), "l"(epoch) : "memory");
-            const unsigned long long* mine = p2p->peer_flag[me] + threadIdx.x;
-            unsigned long long seen = 0;
-            const long long t0 = clock64();
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
-                if (seen >= epoch) break;
-                __nanosleep(32);
-            } while (clock64() - t0 < 4000000000ll);              // ~2 s: a dead peer must not hang the GPU
-            if (seen < epoch) ctl->error = 2;
-        }
-        __syncthreads();
+        __syncthreads();                                  // S.red has been sent before it is overwritten with the sum
         if (threadIdx.x < PSTRIDE) {
-            const double* mail = p2p->peer_mail[me] + (size_t)par * nr * PSTRIDE;
+            const unsigned long long* mail = reinterpret_cast<const unsigned long long*>(p2p->peer_mail[me]) + (size_t)par * nr * PSTRIDE * 2;
             double v = 0.0;
-            for (int r = 0; r < nr; r++) v += __ldcg(&mail[(size_t)r * PSTRIDE + threadIdx.x]);
+            bool late = false;
+            for (int r = 0; r < nr; r++) {
+                const unsigned long long* src = mail + ((size_t)r * PSTRIDE + threadIdx.x) * 2;
+                unsigned long long lo = 0, hi = 0;
+                const long long t0 = clock64();
+                while (true) {
+                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(lo) : "l"(src) : "memory");
+                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(hi) : "l"(src + 1) : "memory");
+                    if ((lo & 0xffffffff00000000ull) == tag && (hi & 0xffffffff00000000ull) == tag) break;
+                    if (clock64() - t0 > 4000000000ll) { late = true; break; }      // ~2 s: a dead peer must not hang the GPU
+                }
+                v += __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+            }
             S.red[threadIdx.x] = v;
+            if (late) ctl->error = 2;
         }
         if (threadIdx.x == 0) p2p->epoch = epoch;
         __syncthreads();
@@ -1377,7 +1385,7 @@ int Filter::get_pass_logs(PassLog* out, int cap, int* n) {
 
 int Filter::p2p_local_handle(void* out64) {
     FL_CUDA(cudaSetDevice(map_->device()));
-    const size_t bytes = sizeof(double) * 2 * P2P_MAX_RANKS * PSTRIDE + sizeof(unsigned long long) * 2 * P2P_MAX_RANKS;   // mail, flags, barrier slots
+    const size_t bytes = P2P_MAIL_BYTES + sizeof(unsigned long long) * 2 * P2P_MAX_RANKS;   // mail, (unused) flags, barrier slots
     if (!mailbox_.ptr) {
         FL_CHECK(mailbox_.reserve(bytes));
         FL_CUDA(cudaMemset(mailbox_.ptr, 0, mailbox_.bytes));
@@ -1405,7 +1413,7 @@ int Filter::p2p_connect(int nranks, int rank, const void* handles64) {
             peer_ptr_[r] = base;
         }
         st.peer_mail[r] = (double*)base;
-        st.peer_flag[r] = (unsigned long long*)((char*)base + sizeof(double) * 2 * P2P_MAX_RANKS * PSTRIDE);
+        st.peer_flag[r] = (unsigned long long*)((char*)base + P2P_MAIL_BYTES);
         st.peer_bar[r] = st.peer_flag[r] + P2P_MAX_RANKS;
     }
     // NOTE the mailbox stride uses P2P_MAX_RANKS rows per parity only for the allocation size; rows are indexed [par * nranks + r]

@@ -54,7 +54,7 @@ struct ScanView {
 struct NcclApi;
 
 // Peer-memory exchange of the per-pass sums (fused into k_residual's solver block): every rank owns a
-// mailbox [2 epochs parity][nranks][96] doubles + nranks epoch flags; peers store into it over NVLink.
+// mailbox [2 epoch parities][nranks][96] values, each two epoch-tagged 8-byte words; peers store into it over NVLink.
 constexpr int P2P_MAX_RANKS = 8;
 struct P2PState {
     double* peer_mail[P2P_MAX_RANKS];                 // mailbox of rank r (mapped through CUDA IPC)

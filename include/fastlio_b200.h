@@ -175,7 +175,8 @@ int fl_filter_comm_init(fl_filter_t* f, int nranks, int rank, const void* unique
 int fl_filter_set_shard(fl_filter_t* f, int q_begin, int q_end);
 /* Same exchange without NCCL, fused into the residual kernel: each rank exports its mailbox as a 64-byte CUDA-IPC
  * handle (fl_filter_p2p_handle), the application all-gathers the handles, fl_filter_p2p_connect maps the peers.
- * Per pass every rank stores its 92 sums straight into its peers' mailboxes over NVLink and spins on epoch flags. */
+ * Per pass every rank stores its 92 sums straight into its peers' mailboxes over NVLink as epoch-tagged 8-byte words
+ * (the data is the flag) and adds the slots of its own mailbox in rank order: every rank ends with the same bits. */
 int fl_filter_p2p_handle(fl_filter_t* f, void* out64);
 int fl_filter_p2p_connect(fl_filter_t* f, int nranks, int rank, const void* handles /* nranks x 64 bytes */);
 

@@ -1,15 +1,17 @@
-// Fused measurement kernel + on-device iterated-EKF solve for FAST-LIO2's per-scan update.
+// The per-scan iterated-EKF measurement update of FAST-LIO2 on the device.  Per pass, two kernels:
 //
-//   k_measure : h_share_model (reference src/laserMapping.cpp:638-754) for all scan points:
-//               body->world transform, k=5 nearest-neighbour search in the device map (search
-//               passes only), 5-point plane fit (esti_plane, include/common_lib.h:225-257),
-//               residual gating, Jacobian row -- and, instead of materialising h_x (m x 12) and
-//               h (m), the FP64 normal equations H^T H (12x12) / H^T h (12) that
-//               update_iterated_dyn_share_modified consumes (esekfom.hpp:1784,1804), reduced with
-//               warp shuffles and one deterministic per-block partial.
-//   k_solve   : esekfom.hpp:1651-1927 -- boxminus, manifold congruences on P, the Kalman gain
-//               algebra, boxplus, convergence bookkeeping, final covariance -- in one thread block,
-//               so that the whole multi-pass update runs without a host round trip.
+//   k_search   : the kNN half of h_share_model (reference src/laserMapping.cpp:656-672): body->world transform and
+//                k = 5 nearest-neighbour search in the device map, one warp per scan point; works only on the passes
+//                for which the filter asks for a search (decided on the device).
+//   k_residual : the rest of h_share_model (:674-752) -- 5-point plane fit (esti_plane, include/common_lib.h:225-257),
+//                residual gating, Jacobian row -- folded straight into the FP64 normal equations H^T H (12x12) /
+//                H^T h (12) that update_iterated_dyn_share_modified consumes (esekfom.hpp:1784,1804), one deterministic
+//                partial per block; block 0 is the solver block and runs esekfom.hpp:1651-1927 (boxminus, manifold
+//                congruences on P, the Kalman gain algebra, boxplus, convergence bookkeeping, final covariance).
+//
+// The kernels of a scan are chained with programmatic dependent launch; the whole multi-pass update runs without a
+// host round trip.  Multi-GPU: scan points are sharded, the 92 sums are exchanged inside k_residual over peer memory
+// (or with NCCL between k_residual and k_solve_only).
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -1250,11 +1252,6 @@ int Filter::launch_residual_only() {
     FL_CUDA(cudaGetLastError());
     return FL_OK;
 }
-int Filter::launch_measure_only() {
-    FL_CHECK(launch_search_only());
-    return launch_residual_only();
-}
-
 int Filter::sync() {
     FL_CUDA(cudaSetDevice(map_->device()));
     FL_CUDA(cudaStreamSynchronize(stream()));

@@ -85,7 +85,6 @@ public:
     int upload_state(const double* x26, const double* P, double R, bool snapshot = true);
     int restore_state();                               // device-side copy of the last uploaded state -> control block
     int run_passes();                                  // enqueue every pass on the stream (no sync)
-    int launch_measure_only();
     int launch_search_only();
     int launch_residual_only();
     int download_state(double* x26, double* P, int* n_pass);

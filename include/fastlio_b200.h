@@ -126,7 +126,7 @@ int fl_filter_time_resident(fl_filter_t* f, int reps, int flush_l2, float* ms_to
  * native code (the per-scan cost a C++ caller such as laserMapping.cpp sees); x26_out / P_out (may be NULL): last result */
 int fl_filter_time_e2e(fl_filter_t* f, const float* body_xyzi, int nq, const double* x26, const double* P, double R, int reps,
                        double* seconds, double* x26_out, double* P_out);
-/* device time of `reps` launches of the dominant kernel alone (k_measure in search mode) */
+/* device time of `reps` launches of the dominant kernel alone (k_search: the kNN of the first pass of an update) */
 int fl_filter_time_search_pass(fl_filter_t* f, int reps, int flush_l2, float* ms_total);
 int fl_filter_gpu_launches(fl_filter_t* f);
 /* clock64() stamps of the last on-device Kalman step (tuning aid; layout in scripts/profile_once.py) */

@@ -121,3 +121,55 @@ def test_A_matrix_matches_series():
     n = np.linalg.norm(v)
     ref = np.eye(3) + (1 - np.cos(n)) / n**2 * K + (1 - np.sin(n) / n) / n**2 * K @ K
     assert np.allclose(out.reshape(3, 3), ref, atol=1e-14)
+
+
+def test_A_matrix_is_the_left_jacobian_of_exp():
+    """Independent of the closed form: Exp(v + dv) ~= Exp(A(v) dv) Exp(v) to first order (scipy's rotation vectors)."""
+    from scipy.spatial.transform import Rotation as Rot
+    L = bind.lib()
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        v = rng.normal(0, 0.3, 3)
+        A = np.zeros(9); L.oracle_A_matrix(v, A); A = A.reshape(3, 3)
+        J = np.zeros((3, 3))
+        eps = 1e-6
+        for a in range(3):
+            dv = np.zeros(3); dv[a] = eps
+            J[:, a] = (Rot.from_rotvec(v + dv) * Rot.from_rotvec(v).inv()).as_rotvec() / eps
+        assert np.allclose(A, J, atol=5e-6)
+
+
+def test_boxplus_is_right_multiplication_by_exp():
+    """SO3 [+] (SOn.hpp:233-236): q [+] d = q * Exp(d); checked against scipy, for rot and offset_R_L_I; vectors add;
+    the S2 gravity keeps its length and moves by ~|d| on the sphere."""
+    from scipy.spatial.transform import Rotation as Rot
+    L = bind.lib()
+    rng = np.random.default_rng(6)
+    x = synth.true_state("velodyne")
+    for _ in range(20):
+        d = rng.normal(0, 0.05, 23)
+        y = x.copy(); L.oracle_state_boxplus(y, d)
+        for xo, do in ((3, 3), (7, 6)):
+            want = (Rot.from_quat(x[xo:xo + 4]) * Rot.from_rotvec(d[do:do + 3])).as_quat()
+            got = y[xo:xo + 4] / np.linalg.norm(y[xo:xo + 4])
+            assert min(np.abs(got - want).max(), np.abs(got + want).max()) < 1e-12
+        assert np.allclose(y[0:3], x[0:3] + d[0:3]) and np.allclose(y[14:17], x[14:17] + d[12:15])
+        ang = np.arccos(np.clip(np.dot(y[23:26], x[23:26]) / synth.G_LEN ** 2, -1, 1))
+        assert abs(ang - np.linalg.norm(d[21:23])) < 1e-3 * max(1.0, np.linalg.norm(d[21:23]) * 1e3)
+
+
+def test_first_pass_equals_the_closed_form_kalman_step(problems):
+    """With x = x_propagated (first pass) every manifold Jacobian is the identity and the pass is a plain Kalman step:
+    dx = (H^T H / R + P^-1)^-1 H^T z / R on the 12 observed DOF (esekfom.hpp:1784-1817).  Recompute it with numpy from
+    the oracle's own H^T H / H^T h of that pass and compare the state it reports after the pass."""
+    pr = problems("small")
+    t = bind.KdTree(pr.map_pts, "port")
+    o = bind.update_iterated(t, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, 0)
+    p0 = o.passes[0]
+    HtH = np.zeros((23, 23)); HtH[:12, :12] = p0["HtH"]
+    Hth = np.zeros(23); Hth[:12] = p0["Hth"]
+    # the model: z = -h (laserMapping.cpp:751 stores h = -pd2), measurement noise R I
+    dx = np.linalg.solve(HtH / pr.R + np.linalg.inv(pr.P_prior), Hth / pr.R)
+    want = pr.x_prior.copy()
+    bind.lib().oracle_state_boxplus(want, np.ascontiguousarray(dx))
+    assert np.abs(want - p0["x_after"]).max() < 1e-9

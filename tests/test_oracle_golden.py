@@ -173,3 +173,45 @@ def test_first_pass_equals_the_closed_form_kalman_step(problems):
     want = pr.x_prior.copy()
     bind.lib().oracle_state_boxplus(want, np.ascontiguousarray(dx))
     assert np.abs(want - p0["x_after"]).max() < 1e-9
+
+
+def test_update_lands_on_the_map_estimate(problems):
+    """An iterated EKF update is Gauss-Newton on  |x [-] x_prior|^2_{P^-1} + sum z_i(x)^2 / R  (FAST-LIO2 eq. 17-20): with the
+    correspondences and planes of the last search pass held fixed, the state the oracle returns must be a stationary point
+    of that cost.  The cost and its gradient are evaluated here with numpy and central differences -- nothing of the
+    update's own Jacobian code is reused -- so a wrong Jacobian row, congruence block or sign would leave a gradient."""
+    pr = problems("small")
+    t = bind.KdTree(pr.map_pts, "port")
+    L = bind.lib()
+    o = bind.update_iterated(t, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, 0)
+    sel = o.selected.astype(bool)
+    assert sel.sum() > 500
+    planes = np.zeros((len(pr.scan), 4))
+    for i in np.flatnonzero(sel):
+        ok, pl = bind.esti_plane(o.nearest[i, :, :3], 0.1)
+        assert ok
+        planes[i] = pl
+    Pinv = np.linalg.inv(pr.P_prior)
+    pts = pr.scan[sel, :3].astype(np.float64)
+    pl = planes[sel]
+
+    def cost(x):
+        r = np.zeros(23)
+        L.oracle_state_boxminus(np.ascontiguousarray(x), pr.x_prior, r)
+        R = synth.quat_to_mat(x[3:7]); Rl = synth.quat_to_mat(x[7:11])
+        pw = (pts @ Rl.T + x[11:14]) @ R.T + x[0:3]
+        z = (pw * pl[:, :3]).sum(axis=1) + pl[:, 3]
+        return r @ Pinv @ r + (z * z).sum() / pr.R
+
+    def grad(x0):
+        g = np.zeros(23)
+        for a in range(23):
+            d = np.zeros(23); d[a] = 1e-6
+            xp = x0.copy(); L.oracle_state_boxplus(xp, d)
+            xm = x0.copy(); L.oracle_state_boxplus(xm, -d)
+            g[a] = (cost(xp) - cost(xm)) / 2e-6
+        return g
+
+    g_prior, g_post = grad(pr.x_prior), grad(o.x)
+    assert cost(o.x) < 0.1 * cost(pr.x_prior)
+    assert np.linalg.norm(g_post) < 1e-5 * np.linalg.norm(g_prior)

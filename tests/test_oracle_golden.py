@@ -215,3 +215,17 @@ def test_update_lands_on_the_map_estimate(problems):
     g_prior, g_post = grad(pr.x_prior), grad(o.x)
     assert cost(o.x) < 0.1 * cost(pr.x_prior)
     assert np.linalg.norm(g_post) < 1e-5 * np.linalg.norm(g_prior)
+
+
+def test_posterior_covariance_is_the_inverse_information(problems):
+    """esekfom.hpp:1834-1927 assembles P = L - K_x P with the manifold congruences; for the small corrections of a scan
+    (|dx| ~ 1e-2) those are the identity to first order, so P must equal (P_prior^-1 + H^T H / R)^-1 with the H^T H of the
+    last pass -- computed here with numpy from the oracle's own normal equations."""
+    pr = problems("small")
+    t = bind.KdTree(pr.map_pts, "port")
+    o = bind.update_iterated(t, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, 0)
+    HtH = np.zeros((23, 23)); HtH[:12, :12] = o.passes[-1]["HtH"]
+    want = np.linalg.inv(np.linalg.inv(pr.P_prior) + HtH / pr.R)
+    scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
+    assert (np.abs(o.P - want) / scale).max() < 1e-4
+    assert np.allclose(o.P, o.P.T, atol=1e-15) and np.linalg.eigvalsh(o.P).min() > 0

@@ -175,7 +175,8 @@ def test_first_pass_equals_the_closed_form_kalman_step(problems):
     assert np.abs(want - p0["x_after"]).max() < 1e-9
 
 
-def test_update_lands_on_the_map_estimate(problems):
+@pytest.mark.parametrize("extr", [0, 1])
+def test_update_lands_on_the_map_estimate(problems, extr):
     """An iterated EKF update is Gauss-Newton on  |x [-] x_prior|^2_{P^-1} + sum z_i(x)^2 / R  (FAST-LIO2 eq. 17-20): with the
     correspondences and planes of the last search pass held fixed, the state the oracle returns must be a stationary point
     of that cost.  The cost and its gradient are evaluated here with numpy and central differences -- nothing of the
@@ -183,7 +184,7 @@ def test_update_lands_on_the_map_estimate(problems):
     pr = problems("small")
     t = bind.KdTree(pr.map_pts, "port")
     L = bind.lib()
-    o = bind.update_iterated(t, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, 0)
+    o = bind.update_iterated(t, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, extr)
     sel = o.selected.astype(bool)
     assert sel.sum() > 500
     planes = np.zeros((len(pr.scan), 4))
@@ -217,15 +218,17 @@ def test_update_lands_on_the_map_estimate(problems):
     assert np.linalg.norm(g_post) < 1e-5 * np.linalg.norm(g_prior)
 
 
-def test_posterior_covariance_is_the_inverse_information(problems):
+@pytest.mark.parametrize("extr", [0, 1])
+def test_posterior_covariance_is_the_inverse_information(problems, extr):
     """esekfom.hpp:1834-1927 assembles P = L - K_x P with the manifold congruences; for the small corrections of a scan
     (|dx| ~ 1e-2) those are the identity to first order, so P must equal (P_prior^-1 + H^T H / R)^-1 with the H^T H of the
     last pass -- computed here with numpy from the oracle's own normal equations."""
     pr = problems("small")
     t = bind.KdTree(pr.map_pts, "port")
-    o = bind.update_iterated(t, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, 0)
+    o = bind.update_iterated(t, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit, extr)
     HtH = np.zeros((23, 23)); HtH[:12, :12] = o.passes[-1]["HtH"]
     want = np.linalg.inv(np.linalg.inv(pr.P_prior) + HtH / pr.R)
     scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
     assert (np.abs(o.P - want) / scale).max() < 1e-4
-    assert np.allclose(o.P, o.P.T, atol=1e-15) and np.linalg.eigvalsh(o.P).min() > 0
+    # the reference never symmetrises P; with extrinsic estimation the barely observable LiDAR-IMU rotation leaves 1e-5-level asymmetry
+    assert (np.abs(o.P - o.P.T) / scale).max() < 1e-4 and np.linalg.eigvalsh(0.5 * (o.P + o.P.T)).min() > 0

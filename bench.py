@@ -135,36 +135,68 @@ def c_stdout_to_stderr():
         os.close(saved)
 
 
-def cpu_update_loop(pr, n_scans: int, nthreads: int, warm: int = 1):
-    """Times the CPU reference path.  The reference's OpenMP loop (laserMapping.cpp:646-650) does not
-    scale to every core count (allocation inside KD_TREE::Nearest_Search), so the thread count is
-    calibrated first -- one scan each at nproc, nproc/2, ... >= 4 -- and the fastest is used: the baseline is
-    the reference's best, not a strawman.  Returns (seconds per scan list, kind, threads used)."""
+_CPU_CAL = {}
+
+
+def cpu_update_loop(pr, n_scans: int, nthreads: int, warm: int = 3):
+    """Times the CPU reference path (the reference's unmodified ikd-Tree + the restated h_share_model / update).
+
+    The reference's OpenMP loop (laserMapping.cpp:646-650) does not scale to every core count (allocation inside
+    KD_TREE::Nearest_Search), so the thread count is calibrated ONCE per process -- 5 scans each at nproc, nproc/2, ...
+    >= 4, the candidate with the best median wins -- with the OpenMP threads pinned (OMP_PROC_BIND / OMP_PLACES are set
+    by main() before any OpenMP runtime starts).  Then `warm` untimed scans and n_scans (>= 20) timed ones; the figure
+    reported is the MEDIAN.  The reference's own default of 3 threads (CMakeLists.txt:23-26: MP_PROC_NUM = 3 on hosts
+    with more than 4 cores) is timed beside it.  Returns a dict."""
     from oracle import bind
     tree = bind.KdTree(pr.map_pts, "auto")
     kind = "reference" if tree.backend == "reference" else "port"
+    last = {}
 
     def one(nt):
         t0 = time.perf_counter()
-        bind.update_iterated(tree, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit,
-                             pr.extrinsic_est_en, nthreads=nt)
+        last["r"] = bind.update_iterated(tree, pr.scan, pr.x_prior, pr.P_prior, pr.cfg.max_iter, pr.R, pr.limit,
+                                         pr.extrinsic_est_en, nthreads=nt)
         return time.perf_counter() - t0
 
     one(nthreads)                                   # warm the tree / page cache
-    cands, nt = [], nthreads
-    while nt >= 4:
-        cands.append(nt)
-        nt //= 2
-    if not cands:
-        cands = [max(1, nthreads)]
-    best = min(cands, key=lambda c: sorted(one(c) for _ in range(3))[1])      # median of three: the host is shared and noisy
-    times = []
-    for i in range(warm + n_scans):
-        dt = one(best)
-        if i >= warm:
-            times.append(dt)
+    key = (pr.cfg.name, nthreads)
+    if key not in _CPU_CAL:
+        cands, nt = [], nthreads
+        while nt >= 4:
+            cands.append(nt)
+            nt //= 2
+        if not cands:
+            cands = [max(1, nthreads)]
+        med = {c: float(np.median([one(c) for _ in range(5)])) for c in cands}
+        _CPU_CAL[key] = (min(cands, key=lambda c: med[c]), med)
+    best, med = _CPU_CAL[key]
+    n_scans = max(20, n_scans)
+    for _ in range(max(3, warm)):
+        one(best)
+    times = [one(best) for _ in range(n_scans)]
+    t3 = [one(3) for _ in range(7)][2:]
+    result = last["r"]
     tree.close()
-    return times, kind, best
+    return {"times": times, "median_s": float(np.median(times)), "mean_s": float(np.mean(times)), "kind": kind, "threads": best,
+            "calibration_ms": {str(c): round(1e3 * v, 2) for c, v in med.items()},
+            "median_s_3_threads": float(np.median(t3)), "x": result.x, "P": result.P}
+
+
+def rot_angle(qa, qb):
+    qa = np.asarray(qa) / np.linalg.norm(qa); qb = np.asarray(qb) / np.linalg.norm(qb)
+    return 2.0 * math.acos(min(1.0, abs(float(np.dot(qa, qb)))))
+
+
+def state_parity(x, P, xo, Po):
+    """North-star tolerance: 1e-4 m / 1e-4 rad on the state, against the CPU reference path's result on the same input."""
+    pos = float(np.abs(x[0:3] - xo[0:3]).max())
+    rot = max(rot_angle(x[3:7], xo[3:7]), rot_angle(x[7:11], xo[7:11]))
+    rest = float(np.abs(x[11:] - xo[11:]).max())
+    scale = np.sqrt(np.outer(np.diag(Po), np.diag(Po)))
+    cov = float((np.abs(P - Po) / scale).max())
+    return {"pos_err": pos, "rot_err": rot, "other_err": rest, "cov_rel_err": cov, "tol": 1e-4,
+            "ok": bool(pos <= 1e-4 and rot <= 1e-4 and rest <= 1e-4 and cov <= 1e-3),
+            "against": "cpu_baseline leg's final state (reference ikd-Tree + restated update), same scan / prior"}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -175,16 +207,19 @@ def run_reference(args, rank: int):
     pr = synth.make_problem(args.workload)
     cores = os.cpu_count() or 1
     with c_stdout_to_stderr():
-        times, kind, cores = cpu_update_loop(pr, args.steps, cores, warm=max(1, args.warmup))
-    total = float(np.sum(times))
-    val = len(times) / total
+        c = cpu_update_loop(pr, args.steps, cores, warm=args.warmup)
+    times = c["times"]
+    val = 1.0 / c["median_s"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": max(3, args.warmup), "ms_per_step": 1e3 * c["median_s"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 geometry / f64 filter", "data": "synthetic",
         "config": {"workload": args.workload, "n_map": pr.cfg.n_map, "n_scan": pr.cfg.n_scan, "max_iteration": pr.cfg.max_iter},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{len(times)} full scan updates of the same workload, OpenMP over scan points, thread count calibrated (best of nproc, nproc/2, ...)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": c["threads"], "kind": c["kind"],
+                         "sample": f"median of {len(times)} full scan updates of the same workload (mean {1e3 * c['mean_s']:.2f} ms), OpenMP over scan points, "
+                                   f"threads pinned, thread count calibrated once (5 scans per candidate: {c['calibration_ms']} ms)",
+                         "host_cores": os.cpu_count(), "value_3_threads": 1.0 / c["median_s_3_threads"],
+                         "note_3_threads": "the reference's compiled-in default MP_PROC_NUM = 3 (CMakeLists.txt:23-26)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -208,7 +243,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     tree = api.KdTree(local_rank, 0.5)
     tree.Build(pr.map_pts)                       # map replicated on every rank
     filt = api.Esekf(tree, max_points=Q, max_iter=pr.cfg.max_iter, limit=pr.limit,
-                     extrinsic_est_en=bool(pr.extrinsic_est_en), solver=args.solver)
+                     extrinsic_est_en=bool(pr.extrinsic_est_en), solver=args.solver, search=args.search)
     if world > 1:
         comm = args.comm
         if comm == "p2p":
@@ -227,7 +262,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             if int(flag.item()) == 0:
                 comm = "nccl"
                 filt = api.Esekf(tree, max_points=Q, max_iter=pr.cfg.max_iter, limit=pr.limit,
-                                 extrinsic_est_en=bool(pr.extrinsic_est_en), solver=args.solver)
+                                 extrinsic_est_en=bool(pr.extrinsic_est_en), solver=args.solver, search=args.search)
         if comm == "nccl":
             uid = [api.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
@@ -298,13 +333,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 traffic = None
         # CPU baseline on a bounded sample (about 10-30 s of CPU work)
         cpu = None
+        parity = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_cpu = max(3, min(40, args.cpu_scans))
             with c_stdout_to_stderr():
-                times, kind, cores = cpu_update_loop(pr, n_cpu, cores, warm=1)
-            cpu = {"value": len(times) / float(np.sum(times)), "unit": UNIT, "cores": cores, "kind": kind,
-                   "sample": f"{len(times)} full scan updates of the same workload (median {1e3 * float(np.median(times)):.1f} ms/scan), thread count calibrated"}
+                c = cpu_update_loop(pr, args.cpu_scans, cores)
+            cpu = {"value": 1.0 / c["median_s"], "unit": UNIT, "cores": c["threads"], "kind": c["kind"],
+                   "sample": f"median of {len(c['times'])} full scan updates of the same workload ({1e3 * c['median_s']:.2f} ms/scan, mean {1e3 * c['mean_s']:.2f}), "
+                             f"threads pinned, thread count calibrated once ({c['calibration_ms']} ms)",
+                   "host_cores": os.cpu_count(), "value_3_threads": 1.0 / c["median_s_3_threads"]}
+            parity = state_parity(x_res, P_res, c["x"], c["P"])
+            parity["e2e_path"] = state_parity(x_e2e, P_e2e, c["x"], c["P"])["ok"]
         line = {
             "metric": METRIC, "value": args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -322,11 +361,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_launch, "launch_ms": ms_search, "launch_ms_l2_warm": ms_search_warm},
             "cpu_baseline": cpu,
+            "parity": parity,
             "clocks": clocks,
             "extra": {"value_l2_warm": args.steps / (ms_warm * 1e-3), "wall_s_timed_region": t_wall,
                       "pos_err_vs_truth_m": float(np.abs(x_res[:3] - pr.x_true[:3]).max())},
         }
         print(json.dumps(line), flush=True)
+        if parity is not None and not (parity["ok"] and parity["e2e_path"]):
+            print("bench.py: the GPU state differs from the CPU reference path beyond 1e-4 -- this number is not valid", file=sys.stderr)
+            return 3
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -341,10 +384,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="velodyne_30k_1m")
     ap.add_argument("--solver", type=int, default=1)
+    ap.add_argument("--search", type=int, default=-1, help="-1: library default; 0: BVH walk; 1: cell directory")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--cpu-scans", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # pin the OpenMP threads of the CPU reference path (must be in the environment before any OpenMP runtime starts)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         return run_reference(args, rank)

@@ -39,7 +39,7 @@ SYMBOLS = [
     "fl_last_error", "fl_device_count", "fl_version", "fl_host_register", "fl_host_unregister", "fl_filter_debug_prof",
     "fl_map_create", "fl_map_destroy", "fl_map_set_downsample", "fl_map_build", "fl_map_size", "fl_map_validnum",
     "fl_map_knn", "fl_map_add_points", "fl_map_delete_boxes", "fl_map_flatten", "fl_map_tree_range",
-    "fl_map_rebuild", "fl_map_stats",
+    "fl_map_rebuild", "fl_map_stats", "fl_map_set_cell_directory", "fl_map_dir_stats",
     "fl_filter_create", "fl_filter_destroy", "fl_filter_set_params", "fl_filter_set_solver", "fl_filter_set_search", "fl_filter_update",
     "fl_filter_map_incremental", "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
     "fl_filter_upload_state", "fl_filter_run", "fl_filter_download_state", "fl_filter_sync",
@@ -79,6 +79,8 @@ def load():
     L.fl_map_tree_range.argtypes = [C.c_void_p, _f32p]
     L.fl_map_rebuild.argtypes = [C.c_void_p]
     L.fl_map_stats.argtypes = [C.c_void_p, _i32p]
+    L.fl_map_set_cell_directory.argtypes = [C.c_void_p, C.c_int, C.c_float]
+    L.fl_map_dir_stats.argtypes = [C.c_void_p, _i32p]
     L.fl_filter_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int]
     L.fl_filter_destroy.argtypes = [C.c_void_p]
     L.fl_filter_set_params.argtypes = [C.c_void_p, C.c_int, _f64p, C.c_int]
@@ -131,11 +133,13 @@ def device_count() -> int:
 class KdTree:
     """Device point map with the KD_TREE<PointType> call surface used by laserMapping.cpp."""
 
-    def __init__(self, device: int = 0, downsample: float = 0.5):
+    def __init__(self, device: int = 0, downsample: float = 0.5, cell_directory: bool = True, cell_size: float = 0.0):
         self._L = load()
         h = C.c_void_p()
         _check(self._L.fl_map_create(C.byref(h), device, downsample))
         self.h = h
+        if not cell_directory or cell_size > 0.0:
+            _check(self._L.fl_map_set_cell_directory(self.h, int(cell_directory), cell_size))
 
     def close(self):
         if getattr(self, "h", None):
@@ -203,12 +207,17 @@ class KdTree:
         _check(self._L.fl_map_stats(self.h, s))
         return dict(main_leaves=int(s[0]), overflow_leaves=int(s[1]), levels=int(s[2]), rebuilds=int(s[3]))
 
+    def dir_stats(self) -> dict:
+        s = np.zeros(6, dtype=np.int32)
+        _check(self._L.fl_map_dir_stats(self.h, s))
+        return dict(cells=int(s[0]), ext_buckets=int(s[1]), crowded_cells=int(s[2]), capacity=int(s[3]), relists=int(s[4]), walked=int(s[5]), enabled=bool(s[5] >= 0))
+
 
 class Esekf:
     """esekf::update_iterated_dyn_share_modified with the fused device measurement model."""
 
     def __init__(self, tree: KdTree, max_points: int = 100000, max_iter: int = 4, limit: float = 0.001,
-                 extrinsic_est_en: bool = False, solver: int = 1, search: int = 0):
+                 extrinsic_est_en: bool = False, solver: int = 1, search: int = -1):
         self._L = load()
         self.tree = tree
         h = C.c_void_p()
@@ -218,7 +227,8 @@ class Esekf:
         lim = np.full(23, limit, dtype=np.float64)
         _check(self._L.fl_filter_set_params(self.h, max_iter, lim, int(extrinsic_est_en)))
         _check(self._L.fl_filter_set_solver(self.h, solver))
-        _check(self._L.fl_filter_set_search(self.h, search))
+        if search >= 0:
+            _check(self._L.fl_filter_set_search(self.h, search))
 
     def close(self):
         if getattr(self, "h", None):

@@ -128,6 +128,17 @@ int fl_map_stats(fl_map_t* m, int* out4) {
     return FL_OK;
 }
 
+int fl_map_set_cell_directory(fl_map_t* m, int on, float cell_size) {
+    MAP_GUARD(m);
+    m->impl->set_cell_directory(on != 0, cell_size > 0.f ? cell_size : 0.f);
+    return m->impl->build_directory();
+}
+int fl_map_dir_stats(fl_map_t* m, int* out6) {
+    MAP_GUARD(m);
+    if (!out6) return FL_ERR_ARG;
+    return m->impl->dir_stats(out6);
+}
+
 // ------------------------------------------------------------------------------------ filter
 #define FILTER_GUARD(f)                                                                        \
     if (!(f) || !(f)->impl) { fl::set_last_error("null filter handle"); return FL_ERR_ARG; }   \

@@ -29,7 +29,7 @@ constexpr int PSTRIDE = 96;          // doubles per partial row (NRED = 92 padde
 // peer mailbox: [2 parities][P2P_MAX_RANKS slots][PSTRIDE values] x two tagged 8-byte words per value
 constexpr size_t P2P_MAIL_BYTES = sizeof(unsigned long long) * 2 * 2 * P2P_MAX_RANKS * PSTRIDE;
 constexpr int SEARCH_THREADS = 256;
-constexpr int SEARCH_T_THREADS = 128;
+constexpr int SEARCH_C_THREADS = 128;
 constexpr int RESID_THREADS = 256;
 constexpr int MAX_LOGS = 16;
 
@@ -780,26 +780,28 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
     STAMP(7);
 }
 
-// k_search_t -- the same search with one THREAD per scan point (tknn_query, map.cuh): identical
-// results, ~3x fewer warp instructions per query; a scan is a single wave of threads.
-__global__ void __launch_bounds__(SEARCH_T_THREADS) k_search_t(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
+// k_search_c -- the same search through the map's hashed cell directory: one LANE per scan point looks at the 27 cells
+// around its point and proves its five neighbours exact; the few points it cannot prove (sparse surroundings, crowded
+// cells) are walked through the BVH by the whole warp (knn_lanes, map.cuh).  Same neighbours, same distances, bit for bit.
+__global__ void __launch_bounds__(SEARCH_C_THREADS) k_search_c(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
     pdl_wait();
     pdl_launch();
     if (ctl->done || !ctl->converge) return;
-    const int q = sc.q_begin + blockIdx.x * SEARCH_T_THREADS + threadIdx.x;
-    if (q >= sc.q_end) return;
-    const PoseS s = load_pose(ctl->x);
-    float wx, wy, wz;
-    body_to_world(s, __ldg(&sc.body[q]), wx, wy, wz);
-    TKBest kb;
-    tknn_query(m, wx, wy, wz, kb);
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < KNN_K; j++) {
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kb.idx[j] >= 0) { p = m.pts[kb.idx[j]]; p.w = m.payload[kb.idx[j]]; cnt++; }
-        sc.nearest[(size_t)q * KNN_K + j] = p;
+    const int lane = threadIdx.x & 31;
+    const int q = sc.q_begin + blockIdx.x * SEARCH_C_THREADS + threadIdx.x;
+    const bool active = q < sc.q_end;
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    if (active) {
+        const PoseS s = load_pose(ctl->x);
+        body_to_world(s, __ldg(&sc.body[q]), wx, wy, wz);
     }
+    TBest kb;
+    knn_lanes(m, active, wx, wy, wz, kb, lane);
+    if (!active) return;
+    float4 p[KNN_K];
+    const int cnt = knn_fetch(m, kb, p);
+#pragma unroll
+    for (int j = 0; j < KNN_K; j++) sc.nearest[(size_t)q * KNN_K + j] = p[j];
     sc.nearest_cnt[q] = cnt;
     sc.selected[q] = (cnt < KNN_K) ? 0 : (kb.d[KNN_K - 1] > 5.0f ? 0 : 1);          // laserMapping.cpp:671
 }
@@ -1084,6 +1086,7 @@ int Filter::init() {
     FL_CUDA(cudaSetDevice(map_->device()));
     if (const char* e = getenv("FASTLIO_B200_NO_PDL")) pdl_ = !(e[0] == '1');      // A/B switches for tuning
     if (const char* e = getenv("FASTLIO_B200_NO_MIRROR")) mirror_ = !(e[0] == '1');
+    if (const char* e = getenv("FASTLIO_B200_SEARCH")) search_mode_ = atoi(e) ? 1 : 0;
     FL_CHECK(ctl_.reserve(sizeof(FilterCtl)));
     FL_CHECK(ctl0_.reserve(sizeof(FilterCtl)));
     FL_CHECK(red_.reserve(sizeof(double) * PSTRIDE));
@@ -1222,8 +1225,8 @@ int Filter::launch_search_only() {
     FL_CUDA(cudaSetDevice(map_->device()));
     const int nq = scan_.q_end - scan_.q_begin;
     if (search_mode_ == 1) {
-        const int tgrid = std::max(1, (nq + SEARCH_T_THREADS - 1) / SEARCH_T_THREADS);
-        FL_CUDA(launch_pdl(k_search_t, tgrid, SEARCH_T_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
+        const int tgrid = std::max(1, (nq + SEARCH_C_THREADS - 1) / SEARCH_C_THREADS);
+        FL_CUDA(launch_pdl(k_search_c, tgrid, SEARCH_C_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
         return FL_OK;
     }
     const int sgrid = std::max(1, std::min(search_grid_max_, (nq * 32 + SEARCH_THREADS - 1) / SEARCH_THREADS));

@@ -124,7 +124,7 @@ private:
     bool mirror_ = true;               // the last pass stores the result into the page-locked host block itself
     bool pdl_ = true;                  // programmatic dependent launch between the kernels of a scan
     int search_occ_ = 5;               // resident k_search blocks per SM the kernel is compiled for
-    int search_mode_ = 0;              // 0: one warp per query (k_search, default); 1: one thread per query (k_search_t, measured 2.8x slower)
+    int search_mode_ = 1;              // 1 (default): one lane per query through the cell directory (k_search_c); 0: one warp per query through the BVH (k_search)
     ScanView scan_;
     DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, plane_, partials_, red_, ctl_, ctl0_, logs_;
     DeviceBuffer mi_world_, mi_flag_add_, mi_flag_no_, mi_list_add_, mi_list_no_, mi_tmp_, mi_counts_;

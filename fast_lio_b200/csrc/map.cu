@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <vector>
 
 #include "map.h"
@@ -37,7 +38,8 @@ void DeviceBuffer::release() {
 }
 
 // counters_ layout
-enum Counter { C_LEAF_USED = 0, C_DELETED, C_ADDED, C_GROUPS, C_NINSERT, C_TOMB, C_ERROR, C_COMPACT, C_COUNT = 16 };
+enum Counter { C_LEAF_USED = 0, C_DELETED, C_ADDED, C_GROUPS, C_NINSERT, C_TOMB, C_ERROR, C_COMPACT,
+               C_DIR_CELLS, C_DIR_EXT, C_DIR_CROWDED, C_DIR_ERROR, C_DIR_WALKED, C_COUNT = 16 };
 
 // ============================================================================= kernels
 // ----------------------------------------------------------------------------- k-d partition build
@@ -218,24 +220,120 @@ __global__ void k_refit_level(MapView m, int k) {
     }
 }
 
-// Batched Nearest_Search: one warp per query.
+// ----------------------------------------------------------------------------- cell directory (map.cuh)
+// find the entry of `key`, claiming a free one if the cell is new; returns its table index
+__device__ __forceinline__ unsigned dir_claim(const CellDir& D, unsigned long long key, int* counters) {
+    unsigned s = cell_slot(key, D.cap);
+    for (unsigned probes = 0; probes < D.cap; probes++) {
+        const unsigned long long old = atomicCAS(&D.tab[s].key, 0ull, key);
+        if (old == 0ull) { atomicAdd(&counters[C_DIR_CELLS], 1); return s; }
+        if (old == key) return s;
+        s = (s + 1 == D.cap) ? 0u : s + 1;
+    }
+    atomicExch(&counters[C_DIR_ERROR], 1);      // table full (the host sizes it so that this cannot happen)
+    return 0xffffffffu;
+}
+__device__ __forceinline__ unsigned long long point_cell_key(const CellDir& D, const float4& p) {
+    return cell_key(cell_coord(p.x, D.inv_cell), cell_coord(p.y, D.inv_cell), cell_coord(p.z, D.inv_cell));
+}
+__device__ __forceinline__ int dir_alloc_ext(const CellDir& D, int* counters) {
+    const int b = atomicAdd(&counters[C_DIR_EXT], 1);
+    if (b >= D.ext_cap) { atomicExch(&counters[C_DIR_ERROR], 1); return -1; }
+    return b;
+}
+
+// (re)build, three passes over the slots / the table so that no thread ever waits for another:
+//   1. every live slot claims its cell and counts itself;  2. cells with more than CELL_INLINE points get an external
+//   bucket, counts restart;  3. every live slot appends its index.
+__global__ void k_dir_count(MapView m, int n_leaf_used, int* counters) {
+    const long long total = (long long)n_leaf_used * LEAF;
+    for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
+        const float4 p = m.pts[slot];
+        if (!slot_valid(p)) continue;
+        const unsigned e = dir_claim(m.dir, point_cell_key(m.dir, p), counters);
+        if (e != 0xffffffffu) atomicAdd(&m.dir.tab[e].cnt, 1);
+    }
+}
+__global__ void k_dir_alloc(MapView m, int* counters) {
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < m.dir.cap; e += gridDim.x * blockDim.x) {
+        CellEntry& E = m.dir.tab[e];
+#pragma unroll
+        for (int j = 0; j < CELL_INLINE; j++) E.idx[j] = -1;
+        if (E.key == 0ull) continue;
+        if (E.cnt > CELL_MAX) atomicAdd(&counters[C_DIR_CROWDED], 1);
+        if (E.cnt > CELL_INLINE) E.ext = dir_alloc_ext(m.dir, counters) + 1;
+        E.cnt = 0;
+    }
+}
+__global__ void k_dir_fill(MapView m, int n_leaf_used) {
+    const long long total = (long long)n_leaf_used * LEAF;
+    for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
+        const float4 p = m.pts[slot];
+        if (!slot_valid(p)) continue;
+        const unsigned long long key = point_cell_key(m.dir, p);
+        unsigned s = cell_slot(key, m.dir.cap);
+        unsigned probes = 0;
+        while (m.dir.tab[s].key != key && probes < m.dir.cap) { s = (s + 1 == m.dir.cap) ? 0u : s + 1; probes++; }       // present since pass 1
+        if (probes >= m.dir.cap) continue;
+        CellEntry& E = m.dir.tab[s];
+        const int pos = atomicAdd(&E.cnt, 1);
+        if (pos < CELL_INLINE) E.idx[pos] = (int)slot;
+        else if (pos < CELL_MAX && E.ext > 0) m.dir.ext[(size_t)(E.ext - 1) * CELL_EXT + pos - CELL_INLINE] = (int)slot;
+    }
+}
+// incremental: one thread (lane 0 of the inserting warp) lists a freshly written slot under its cell
+__device__ __forceinline__ void dir_add(const MapView& m, const float4& p, int slot, int* counters) {
+    const CellDir& D = m.dir;
+    if (D.cap == 0u) return;
+    const unsigned e = dir_claim(D, point_cell_key(D, p), counters);
+    if (e == 0xffffffffu) return;
+    CellEntry& E = D.tab[e];
+    // a slot that is being re-used may still be listed under this very cell: never list it twice
+    const int seen = min(atomicAdd(&E.cnt, 0), CELL_MAX);
+    for (int j = 0; j < seen; j++) {
+        int v;
+        if (j < CELL_INLINE) v = *(volatile int*)&E.idx[j];
+        else { const int x = *(volatile int*)&E.ext; v = x > 0 ? *(volatile int*)&D.ext[(size_t)(x - 1) * CELL_EXT + j - CELL_INLINE] : -1; }
+        if (v == slot) return;
+    }
+    const int pos = atomicAdd(&E.cnt, 1);
+    if (pos < CELL_INLINE) { *(volatile int*)&E.idx[pos] = slot; return; }
+    if (pos >= CELL_MAX) { if (pos == CELL_MAX) atomicAdd(&counters[C_DIR_CROWDED], 1); return; }
+    int x;
+    if (pos == CELL_INLINE) {                   // the fifth point of the cell brings the external bucket
+        x = dir_alloc_ext(D, counters) + 1;
+        if (x <= 0) return;                     // pool exhausted: the host grows the pool and rebuilds the directory
+        atomicExch(&E.ext, x);
+    } else {
+        const long long t0 = clock64();
+        while ((x = atomicAdd(&E.ext, 0)) == 0) {       // published by the warp that appended the fifth point
+            if (atomicAdd(&counters[C_DIR_ERROR], 0) || clock64() - t0 > 200000000ll) { atomicExch(&counters[C_DIR_ERROR], 1); return; }
+        }
+    }
+    *(volatile int*)&D.ext[(size_t)(x - 1) * CELL_EXT + pos - CELL_INLINE] = slot;
+}
+
+// Batched Nearest_Search: one lane per query (cell directory), BVH walk for what that cannot prove.
 __global__ void __launch_bounds__(256) k_knn_batch(MapView m, const float4* __restrict__ q, int nq, int k,
                                                     float4* __restrict__ out_pts, float* __restrict__ out_d2,
                                                     int* __restrict__ out_cnt) {
     const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += warps) {
-        const float4 qq = __ldg(&q[i]);
-        KBest kb;
-        knn_query(m, qq.x, qq.y, qq.z, kb, lane);
-        const int cnt = min(k, __popc(__ballot_sync(FULL, lane < KNN_K && kb.idx >= 0)));
-        if (lane < k) {
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kb.idx >= 0) { p = m.pts[kb.idx]; p.w = m.payload[kb.idx]; }
-            out_pts[(size_t)i * k + lane] = p;
-            out_d2[(size_t)i * k + lane] = kb.d;
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < nq; base += stride) {
+        const int i = base + lane;
+        const bool active = i < nq;
+        float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) qq = __ldg(&q[i]);
+        TBest kb;
+        knn_lanes(m, active, qq.x, qq.y, qq.z, kb, lane);
+        if (!active) continue;
+        float4 p[KNN_K];
+        const int cnt = knn_fetch(m, kb, p);
+#pragma unroll
+        for (int j = 0; j < KNN_K; j++) {
+            if (j < k) { out_pts[(size_t)i * k + j] = p[j]; out_d2[(size_t)i * k + j] = kb.d[j]; }
         }
-        if (lane == 0) out_cnt[i] = cnt;
+        out_cnt[i] = min(k, cnt);
     }
 }
 
@@ -453,6 +551,7 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
                     if (lane == 0) {
                         m.payload[leaf * LEAF + s] = p.w;
                         m.pts[leaf * LEAF + s] = make_float4(p.x, p.y, p.z, __int_as_float(1));
+                        dir_add(m, p, leaf * LEAF + s, counters);
                     }
                     placed = true;
                 } else {
@@ -498,7 +597,7 @@ Map::Map(int device, float downsample_size) : device_(device), downsample_(downs
 
 Map::~Map() {
     cudaSetDevice(device_);
-    pts_.release(); payload_.release(); next_.release(); counters_.release();
+    pts_.release(); payload_.release(); next_.release(); counters_.release(); dir_tab_.release(); dir_ext_.release();
     for (int k = 0; k < MAX_LEVELS; k++) ebox_[k].release();
     segid_.release(); segtab_[0].release(); segtab_[1].release(); bbox_.release();
     src_.release(); keys_in_.release(); keys_out_.release(); vals_in_.release(); vals_out_.release();
@@ -513,6 +612,9 @@ int Map::init() {
     FL_CHECK(counters_.reserve(sizeof(int) * C_COUNT));
     FL_CUDA(cudaMemsetAsync(counters_.ptr, 0, sizeof(int) * C_COUNT, stream_));
     FL_CUDA(cudaMallocHost(&h_counters_, sizeof(int) * C_COUNT));
+    memset(h_counters_, 0, sizeof(int) * C_COUNT);
+    if (const char* e = getenv("FASTLIO_B200_NO_CELLDIR")) dir_enabled_ = !(e[0] == '1');      // A/B: BVH walk only
+    if (const char* e = getenv("FASTLIO_B200_CELL")) cell_override_ = (float)atof(e);           // A/B: cell edge in metres
     // an empty map: one empty leaf under a one-level root, so that every kernel is well defined
     FL_CHECK(src_.reserve(sizeof(float4)));
     return build_from_sorted(src_.as<float4>(), 0);
@@ -616,6 +718,62 @@ int Map::build_from_sorted(const float4* d_src, int n) {
     n_valid_ = n;
     n_tomb_ = 0;
     built_ = true;
+    return build_directory();
+}
+
+// (Re)build the cell directory over the live slots.  The table is sized from the point count and re-sized when the
+// cells turn out to be more numerous than guessed (load factor kept below ~0.6); the external-bucket pool likewise.
+int Map::build_directory() {
+    FL_CUDA(cudaSetDevice(device_));
+    if (!dir_enabled_) { v_.dir.cap = 0; return FL_OK; }
+    const float cell = cell_override_ > 0.f ? cell_override_ : (downsample_ > 0.f ? 2.f * downsample_ : 1.f);
+    const int used = h_counters_[C_LEAF_USED];
+    size_t want_cap = std::max<size_t>(dir_min_cap_, std::max<size_t>(8192, (size_t)n_valid_ + (size_t)n_valid_ / 4));
+    size_t want_ext = std::max<size_t>(dir_min_ext_, std::max<size_t>(4096, (size_t)n_valid_ / 4));
+    int* d_cnt = counters_.as<int>();
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if (want_cap > 0xfffffff0ull / 2) { set_last_error("cell directory too large"); return FL_ERR_CAPACITY; }
+        FL_CHECK(dir_tab_.reserve(sizeof(CellEntry) * want_cap));
+        FL_CHECK(dir_ext_.reserve(sizeof(int) * CELL_EXT * want_ext));
+        v_.dir.tab = dir_tab_.as<CellEntry>();
+        v_.dir.ext = dir_ext_.as<int>();
+        v_.dir.cap = (unsigned)(dir_tab_.bytes / sizeof(CellEntry));
+        v_.dir.ext_cap = (int)std::min<size_t>(dir_ext_.bytes / (sizeof(int) * CELL_EXT), 0x7fffffff);
+        v_.dir.cell = cell;
+        v_.dir.inv_cell = 1.0f / cell;
+        v_.dir.n_walked = &d_cnt[C_DIR_WALKED];
+        FL_CUDA(cudaMemsetAsync(dir_tab_.ptr, 0, sizeof(CellEntry) * (size_t)v_.dir.cap, stream_));
+        FL_CUDA(cudaMemsetAsync(dir_ext_.ptr, 0xff, sizeof(int) * CELL_EXT * (size_t)v_.dir.ext_cap, stream_));
+        FL_CUDA(cudaMemsetAsync(&d_cnt[C_DIR_CELLS], 0, sizeof(int) * 4, stream_));      // CELLS, EXT, CROWDED, ERROR
+        const int nb = blocks_for((long long)used * LEAF, 256);
+        k_dir_count<<<nb, 256, 0, stream_>>>(v_, used, d_cnt);
+        k_dir_alloc<<<blocks_for(v_.dir.cap, 256), 256, 0, stream_>>>(v_, d_cnt);
+        k_dir_fill<<<nb, 256, 0, stream_>>>(v_, used);
+        FL_CUDA(cudaGetLastError());
+        FL_CUDA(cudaMemcpyAsync(&h_counters_[C_DIR_CELLS], &d_cnt[C_DIR_CELLS], sizeof(int) * 4, cudaMemcpyDeviceToHost, stream_));
+        FL_CUDA(cudaStreamSynchronize(stream_));
+        const size_t cells = (size_t)h_counters_[C_DIR_CELLS];
+        const bool ext_short = h_counters_[C_DIR_ERROR] != 0;
+        const bool crowded_tab = cells * 10 > (size_t)v_.dir.cap * 6;
+        if (!ext_short && !crowded_tab) return FL_OK;
+        if (ext_short) want_ext = std::max<size_t>(want_ext * 2, (size_t)h_counters_[C_DIR_EXT] + 4096);
+        if (crowded_tab) want_cap = cells * 5 / 2 + 8192;
+    }
+    set_last_error("cell directory: could not size the table");
+    return FL_ERR_CAPACITY;
+}
+
+int Map::dir_stats(int* out6) const {
+    // [5]: queries answered by the BVH walk since the last call (0 when the directory is off: every query walks)
+    int walked = 0;
+    if (v_.dir.cap) {
+        cudaSetDevice(device_);
+        cudaMemcpyAsync(&walked, &counters_.as<int>()[C_DIR_WALKED], sizeof(int), cudaMemcpyDeviceToHost, stream_);
+        cudaMemsetAsync(&counters_.as<int>()[C_DIR_WALKED], 0, sizeof(int), stream_);
+        cudaStreamSynchronize(stream_);
+    }
+    out6[0] = h_counters_[C_DIR_CELLS]; out6[1] = h_counters_[C_DIR_EXT]; out6[2] = h_counters_[C_DIR_CROWDED];
+    out6[3] = (int)v_.dir.cap; out6[4] = n_dir_rebuilds_; out6[5] = v_.dir.cap ? walked : -1;
     return FL_OK;
 }
 
@@ -641,7 +799,7 @@ int Map::knn(const float* q_xyzi, int nq, int k, float* out_pts, float* out_d2, 
     char* base = scratch_.as<char>();
     float4* d_q = (float4*)base; float4* d_p = (float4*)(base + qb); float* d_d = (float*)(base + qb + pb); int* d_c = (int*)(base + qb + pb + db);
     FL_CUDA(cudaMemcpyAsync(d_q, q_xyzi, qb, cudaMemcpyHostToDevice, stream_));
-    k_knn_batch<<<blocks_for((long long)nq * 32, 256), 256, 0, stream_>>>(v_, d_q, nq, k, d_p, d_d, d_c);
+    k_knn_batch<<<blocks_for(nq, 256), 256, 0, stream_>>>(v_, d_q, nq, k, d_p, d_d, d_c);
     FL_CUDA(cudaGetLastError());
     FL_CUDA(cudaMemcpyAsync(out_pts, d_p, pb, cudaMemcpyDeviceToHost, stream_));
     FL_CUDA(cudaMemcpyAsync(out_d2, d_d, db, cudaMemcpyDeviceToHost, stream_));
@@ -720,12 +878,27 @@ int Map::insert_device(const float4* d_pts, int n) {
         min_pool_ = std::max(min_pool_, n + 1024);
         FL_CHECK(rebuild());            // re-packs the leaves and re-sizes the pool
     }
+    if (v_.dir.cap) {       // room for n new cells and n new external buckets, so that the insert kernel can never run the table full
+        const size_t cells = (size_t)h_counters_[C_DIR_CELLS] + (size_t)n, ext = (size_t)h_counters_[C_DIR_EXT] + (size_t)n;
+        if (cells * 10 > (size_t)v_.dir.cap * 7 || ext > (size_t)v_.dir.ext_cap) {
+            dir_min_cap_ = std::max(dir_min_cap_, cells * 5 / 2 + 8192);
+            dir_min_ext_ = std::max(dir_min_ext_, ext + ext / 2 + 4096);
+            n_dir_rebuilds_++;
+            FL_CHECK(build_directory());
+        }
+    }
     k_insert<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, n, counters_.as<int>());
     FL_CUDA(cudaGetLastError());
     FL_CUDA(cudaMemcpyAsync(h_counters_, counters_.ptr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, stream_));
     FL_CUDA(cudaStreamSynchronize(stream_));
     if (h_counters_[C_ERROR]) { set_last_error("insert: overflow pool exhausted"); return FL_ERR_CAPACITY; }
     n_valid_ += n;
+    // directory: out of table room / external buckets, or too many crowded cells (stale entries pile up) -> re-list the live slots
+    if (v_.dir.cap) {
+        const bool full = (size_t)h_counters_[C_DIR_CELLS] * 10 > (size_t)v_.dir.cap * 7;
+        const bool crowded = h_counters_[C_DIR_CROWDED] > std::max(64, h_counters_[C_DIR_CELLS] / 64);
+        if (h_counters_[C_DIR_ERROR] || full || crowded) { n_dir_rebuilds_++; FL_CHECK(build_directory()); }
+    }
     return FL_OK;
 }
 

@@ -24,7 +24,37 @@
 
 namespace fl {
 
+// ----------------------------------------------------------------------------- cell directory
+// A hashed directory of cubic cells over the SAME leaf slots: cell (ix, iy, iz) = floor(p * inv_cell) lists the slot
+// indices of the points that were inserted into it.  It is the fast path of the k-NN search (one THREAD per query looks
+// at the 27 cells around it and proves the result exact from the distance to the faces of that block); whatever it
+// cannot prove -- sparse surroundings, crowded cells -- goes through the warp-cooperative BVH walk below, so the result
+// is always the exact answer of KD_TREE::Nearest_Search (ikd_Tree.cpp:426-461).  Validity lives in the slot's flag
+// only (a deleted point is skipped, nothing to update here); a slot re-used by a later insert may leave a stale index
+// behind, which the membership test of the scan rejects.
+constexpr int CELL_INLINE = 4;                     // slot indices stored in the directory entry itself (same 32-byte sector as the key)
+constexpr int CELL_EXT = 16;                       // further indices in the cell's external bucket (64 B)
+constexpr int CELL_MAX = CELL_INLINE + CELL_EXT;   // a cell listing more than this sends its queries to the BVH walk
+constexpr int CELL_OFF = 1 << 20;                  // 21 bits per axis
+constexpr int CELL_CLAMP = (1 << 20) - 4;
+
+struct __align__(32) CellEntry {
+    unsigned long long key;      // 0 = free, else cell_key()
+    int ext;                     // external bucket index + 1 (0 = none yet)
+    int cnt;                     // indices appended so far (may exceed CELL_MAX: overflow)
+    int idx[CELL_INLINE];
+};
+struct CellDir {
+    CellEntry* tab;              // [cap]
+    int* ext;                    // [ext_cap * CELL_EXT]
+    unsigned cap;                // 0: directory disabled
+    int ext_cap;
+    float cell, inv_cell;
+    int* n_walked;               // statistics: queries that went through the BVH walk
+};
+
 struct MapView {
+    CellDir dir;
     float4* pts;                     // [leaf_cap * 32]  (x, y, z, as_float(flag)); flag 1 = valid
     float* payload;                  // [leaf_cap * 32]  intensity of the point in that slot
     int* next;                       // [leaf_cap]       overflow chain of a leaf, -1 = none
@@ -234,25 +264,40 @@ __device__ __forceinline__ void box_query(const MapView& m, const float* bmin, c
 
 }  // namespace fl
 
-// ============================================================================= thread-per-query traversal
-// Same tree, same arithmetic, same result as knn_query -- but one THREAD per query.  A warp-per-
-// query walk spends most of its instructions on lanes whose child box is pruned (32 boxes tested,
-// ~1.3 useful) and on warp-wide ranking; with one query per lane every lane does useful work and
-// the only loss is divergence between neighbouring queries.  MEASURED (B200, 30k queries vs 1M points):
-// 112.7 us against 39.6 us for the warp-per-query kernel -- every load instruction touches 32 different
-// 16-byte sectors (32 L1 wavefronts), which costs more than the idle lanes of the cooperative walk.
-// Kept as a selectable alternative (fl_filter_set_search) and as evidence for the design choice.
+// ============================================================================= cell directory: search
+// One THREAD per query over the hashed cell directory, exact by construction:
+//   * the 27 cells around the query are scanned nearest-first (own cell, faces, edges, corners); a cell is skipped when
+//     its nearest face is not closer than the current k-th best;
+//   * every point OUTSIDE the 3x3x3 block is at least g = (distance from the query to the block's faces) away, so the k
+//     best found are final when the k-th squared distance is strictly below g^2 (strict: the reference keeps the first of
+//     two equidistant candidates, ikd_Tree.cpp:1088) -- tests/cell_directory_model.py pins the rule on the CPU;
+//   * anything else (fewer than k points nearby, a crowded cell, coordinates beyond the key range) is NOT answered here:
+//     knn_lanes() hands those queries to the warp-cooperative BVH walk (knn_query), one at a time.
+// Squared distances use the same explicitly rounded float32 arithmetic as the BVH walk (sq_dist3), so either route
+// returns bit-identical distances.  All margins shrink the proven radius, never the searched set.
 namespace fl {
 
-struct TKBest {                      // ascending, replicated per thread
+__device__ __forceinline__ int cell_coord(float x, float inv_cell) {
+    const float f = floorf(__fmul_rn(x, inv_cell));
+    return (int)fminf(fmaxf(f, -(float)CELL_CLAMP), (float)CELL_CLAMP);
+}
+__host__ __device__ __forceinline__ unsigned long long cell_key(int ix, int iy, int iz) {
+    return (1ull << 63) | ((unsigned long long)(unsigned)(ix + CELL_OFF) << 42) | ((unsigned long long)(unsigned)(iy + CELL_OFF) << 21) |
+           (unsigned long long)(unsigned)(iz + CELL_OFF);
+}
+__device__ __forceinline__ unsigned cell_slot(unsigned long long key, unsigned cap) {
+    const unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+    return __umulhi((unsigned)(h >> 32) ^ (unsigned)h, cap);
+}
+
+struct TBest {                       // k best of one thread, ascending; empty entries: (+inf, -1)
     float d[KNN_K];
     int idx[KNN_K];
     __device__ __forceinline__ void init() {
 #pragma unroll
         for (int i = 0; i < KNN_K; i++) { d[i] = INFINITY; idx[i] = -1; }
     }
-    __device__ __forceinline__ float w() const { return d[KNN_K - 1]; }
-    __device__ __forceinline__ void insert(float nd, int nidx) {       // nd < d[K-1]
+    __device__ __forceinline__ void insert(float nd, int nidx) {       // nd < d[K-1]; equal distances keep their arrival order
 #pragma unroll
         for (int i = KNN_K - 1; i > 0; i--) {
             const bool shift = nd < d[i - 1];
@@ -264,76 +309,130 @@ struct TKBest {                      // ascending, replicated per thread
     }
 };
 
-__device__ __forceinline__ void tknn_leaf(const MapView& m, int leaf, float qx, float qy, float qz, TKBest& kb) {
-    while (leaf >= 0) {
-        const float4* base = m.pts + (size_t)leaf * LEAF;
-#pragma unroll 4
-        for (int s = 0; s < LEAF; s++) {
-            const float4 p = __ldg(&base[s]);
-            if (slot_valid(p)) {
-                const float d = sq_dist3(qx, qy, qz, p.x, p.y, p.z);
-                if (d < kb.w()) kb.insert(d, leaf * LEAF + s);
-            }
-        }
-        leaf = __ldg(&m.next[leaf]);
+// own cell, 6 faces, 12 edges, 8 corners
+static __constant__ signed char CELL_ORDER[27][4] = {
+    {0, 0, 0, 0},
+    {-1, 0, 0, 0}, {1, 0, 0, 0}, {0, -1, 0, 0}, {0, 1, 0, 0}, {0, 0, -1, 0}, {0, 0, 1, 0},
+    {-1, -1, 0, 0}, {-1, 1, 0, 0}, {1, -1, 0, 0}, {1, 1, 0, 0}, {-1, 0, -1, 0}, {-1, 0, 1, 0}, {1, 0, -1, 0}, {1, 0, 1, 0},
+    {0, -1, -1, 0}, {0, -1, 1, 0}, {0, 1, -1, 0}, {0, 1, 1, 0},
+    {-1, -1, -1, 0}, {-1, -1, 1, 0}, {-1, 1, -1, 0}, {-1, 1, 1, 0}, {1, -1, -1, 0}, {1, -1, 1, 0}, {1, 1, -1, 0}, {1, 1, 1, 0}};
+
+__device__ __forceinline__ void cell_consider(const MapView& m, int idx, int cx, int cy, int cz, float qx, float qy, float qz, TBest& kb) {
+    const float4 p = __ldg(&m.pts[idx]);
+    const float inv = m.dir.inv_cell;
+    // the slot must still hold a live point of THIS cell (deleted points keep their entry; re-used slots leave stale ones)
+    if (slot_valid(p) && cell_coord(p.x, inv) == cx && cell_coord(p.y, inv) == cy && cell_coord(p.z, inv) == cz) {
+        const float dd = sq_dist3(qx, qy, qz, p.x, p.y, p.z);
+        if (dd < kb.d[KNN_K - 1]) kb.insert(dd, idx);
     }
 }
 
-// children of `node` at level L (entities of level L-1), visited in ascending (distance, index)
-// order; the runner-up of a scan is remembered so that the usual "nearest child, then nothing
-// else qualifies" case needs a single pass over the boxes.
-template <int L>
-__device__ __forceinline__ void tknn_node(const MapView& m, int first, int n_child, float qx, float qy, float qz, TKBest& kb) {
-    const float4* boxes = m.ebox[L - 1] + 2 * (size_t)first;
-    unsigned long long last = 0ull;          // keys are > 0: (distance bits + 1) << 6 | child
-    unsigned long long runner = ~0ull;
-    bool have_runner = false;
+// scan one cell; sets `crowded` when the cell lists more points than the directory holds
+__device__ __forceinline__ void cell_scan(const MapView& m, int cx, int cy, int cz, float qx, float qy, float qz, TBest& kb, bool& crowded) {
+    const CellDir& D = m.dir;
+    const unsigned long long key = cell_key(cx, cy, cz);
+    unsigned s = cell_slot(key, D.cap);
+    const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
+    uint4 a;
+    unsigned probes = 0;
     while (true) {
-        unsigned long long best = ~0ull;
-        if (have_runner) {
-            best = runner; have_runner = false;
-            // the runner-up's box distance has not changed; only the bound has
-            if (__uint_as_float((unsigned)((best >> 6) - 1ull)) >= kb.w()) break;   // and every other child is farther
-        } else {
-            runner = ~0ull;
-#pragma unroll 4
-            for (int c = 0; c < n_child; c++) {
-                const float4 lo = __ldg(&boxes[2 * c]), hi = __ldg(&boxes[2 * c + 1]);
-                const float d = box_dist3(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-                if (d < kb.w()) {
-                    const unsigned long long key = (((unsigned long long)__float_as_uint(d) + 1ull) << 6) | (unsigned long long)c;
-                    if (key > last) {
-                        if (key < best) { runner = best; best = key; }
-                        else if (key < runner) runner = key;
-                    }
+        a = __ldg(&tab[2 * (size_t)s]);
+        const unsigned long long k = (unsigned long long)a.x | ((unsigned long long)a.y << 32);
+        if (k == key) break;
+        if (k == 0ull) return;
+        if (++probes >= D.cap) { crowded = true; return; }          // cannot happen (load factor < 0.7); never spin
+        s = (s + 1 == D.cap) ? 0u : s + 1;
+    }
+    const int cnt = (int)a.w;
+    if (cnt > CELL_MAX || (cnt > CELL_INLINE && a.z == 0u)) { crowded = true; return; }
+    const uint4 b = __ldg(&tab[2 * (size_t)s + 1]);
+    if (cnt > 0) cell_consider(m, (int)b.x, cx, cy, cz, qx, qy, qz, kb);
+    if (cnt > 1) cell_consider(m, (int)b.y, cx, cy, cz, qx, qy, qz, kb);
+    if (cnt > 2) cell_consider(m, (int)b.z, cx, cy, cz, qx, qy, qz, kb);
+    if (cnt > 3) cell_consider(m, (int)b.w, cx, cy, cz, qx, qy, qz, kb);
+    if (cnt > CELL_INLINE) {
+        const int* ext = D.ext + (size_t)((int)a.z - 1) * CELL_EXT;
+#pragma unroll 1
+        for (int j = 0; j < cnt - CELL_INLINE; j++) cell_consider(m, __ldg(&ext[j]), cx, cy, cz, qx, qy, qz, kb);
+    }
+}
+
+// k-NN of one query by one thread.  Returns true when kb is PROVEN to be the exact answer.
+__device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, float qz, TBest& kb) {
+    const CellDir& D = m.dir;
+    kb.init();
+    if (D.cap == 0u) return false;
+    const int ix = cell_coord(qx, D.inv_cell), iy = cell_coord(qy, D.inv_cell), iz = cell_coord(qz, D.inv_cell);
+    if (abs(ix) >= CELL_CLAMP - 1 || abs(iy) >= CELL_CLAMP - 1 || abs(iz) >= CELL_CLAMP - 1) return false;
+    const float c = D.cell;
+    // distance from the query to the low / high face of its own cell, shrunk by more than any rounding of the cell arithmetic
+    const float marg = 4e-6f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 2.f * c);
+    const float lox = fmaxf(qx - (float)ix * c - marg, 0.f), hix = fmaxf((float)(ix + 1) * c - qx - marg, 0.f);
+    const float loy = fmaxf(qy - (float)iy * c - marg, 0.f), hiy = fmaxf((float)(iy + 1) * c - qy - marg, 0.f);
+    const float loz = fmaxf(qz - (float)iz * c - marg, 0.f), hiz = fmaxf((float)(iz + 1) * c - qz - marg, 0.f);
+    bool crowded = false;
+#pragma unroll 1
+    for (int t = 0; t < 27; t++) {
+        const int dx = CELL_ORDER[t][0], dy = CELL_ORDER[t][1], dz = CELL_ORDER[t][2];
+        const float gx = dx < 0 ? lox : (dx > 0 ? hix : 0.f);
+        const float gy = dy < 0 ? loy : (dy > 0 ? hiy : 0.f);
+        const float gz = dz < 0 ? loz : (dz > 0 ? hiz : 0.f);
+        if (gx * gx + gy * gy + gz * gz < kb.d[KNN_K - 1]) cell_scan(m, ix + dx, iy + dy, iz + dz, qx, qy, qz, kb, crowded);
+    }
+    if (crowded || kb.idx[KNN_K - 1] < 0) return false;
+    const float g = fminf(fminf(fminf(lox, hix), fminf(loy, hiy)), fminf(loz, hiz)) + c - marg;
+    return kb.d[KNN_K - 1] < g * g;
+}
+
+// Exact k-NN for up to 32 queries of a warp (one per lane; `active` masks the tail).  The thread search answers what it
+// can prove; the rest goes through the cooperative BVH walk, one query at a time, and is handed back to its lane.
+__device__ __forceinline__ void knn_lanes(const MapView& m, bool active, float qx, float qy, float qz, TBest& kb, int lane) {
+    bool exact = true;
+    if (active) exact = cell_knn(m, qx, qy, qz, kb);
+    else kb.init();
+    unsigned todo = __ballot_sync(FULL, active && !exact);
+    if (todo && lane == 0 && m.dir.n_walked) atomicAdd(m.dir.n_walked, __popc(todo));
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float fx = __shfl_sync(FULL, qx, src), fy = __shfl_sync(FULL, qy, src), fz = __shfl_sync(FULL, qz, src);
+        KBest w;
+        knn_query(m, fx, fy, fz, w, lane);
+#pragma unroll
+        for (int j = 0; j < KNN_K; j++) {
+            const float dj = __shfl_sync(FULL, w.d, j);
+            const int ij = __shfl_sync(FULL, w.idx, j);
+            if (lane == src) { kb.d[j] = dj; kb.idx[j] = ij; }
+        }
+    }
+}
+
+// The neighbours as the caller sees them: coordinates + intensity, nearest first; candidates whose squared distances
+// differ by less than 1e-10 are ordered by x like PointType_CMP does for the reference's heap (ikd_Tree.h:102-108).
+__device__ __forceinline__ int knn_fetch(const MapView& m, TBest& kb, float4 (&p)[KNN_K]) {
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < KNN_K; j++) {
+        p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kb.idx[j] >= 0) { p[j] = __ldg(&m.pts[kb.idx[j]]); p[j].w = __ldg(&m.payload[kb.idx[j]]); cnt++; }
+    }
+    bool tie = false;
+#pragma unroll
+    for (int j = 0; j + 1 < KNN_K; j++) tie |= kb.idx[j + 1] >= 0 && fabsf(kb.d[j + 1] - kb.d[j]) < 1e-10f;
+    if (tie) {
+#pragma unroll
+        for (int pass = 0; pass < KNN_K - 1; pass++) {
+#pragma unroll
+            for (int j = 0; j + 1 < KNN_K - pass; j++) {
+                if (kb.idx[j + 1] >= 0 && fabsf(kb.d[j + 1] - kb.d[j]) < 1e-10f && p[j + 1].x < p[j].x) {
+                    const float4 tp = p[j]; p[j] = p[j + 1]; p[j + 1] = tp;
+                    const float td = kb.d[j]; kb.d[j] = kb.d[j + 1]; kb.d[j + 1] = td;
+                    const int ti = kb.idx[j]; kb.idx[j] = kb.idx[j + 1]; kb.idx[j + 1] = ti;
                 }
             }
-            if (best == ~0ull) break;
-            have_runner = runner != ~0ull;
-        }
-        last = best;
-        const int c = (int)(best & 63ull);
-        if constexpr (L == 1) tknn_leaf(m, first + c, qx, qy, qz, kb);
-        else {
-            const int child = first + c;
-            const int cnt = min(FAN, m.count[L - 2] - child * FAN);
-            tknn_node<L - 1>(m, child * FAN, cnt, qx, qy, qz, kb);
         }
     }
-}
-
-__device__ __forceinline__ void tknn_query(const MapView& m, float qx, float qy, float qz, TKBest& kb) {
-    kb.init();
-    const int top = m.count[m.n_levels - 1];          // the root owns up to 64 entities
-    switch (m.n_levels) {
-        case 1: tknn_node<1>(m, 0, top, qx, qy, qz, kb); break;
-        case 2: tknn_node<2>(m, 0, top, qx, qy, qz, kb); break;
-        case 3: tknn_node<3>(m, 0, top, qx, qy, qz, kb); break;
-        case 4: tknn_node<4>(m, 0, top, qx, qy, qz, kb); break;
-        case 5: tknn_node<5>(m, 0, top, qx, qy, qz, kb); break;
-        default: tknn_node<6>(m, 0, top, qx, qy, qz, kb); break;
-    }
+    return cnt;
 }
 
 }  // namespace fl
-

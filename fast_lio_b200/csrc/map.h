@@ -36,6 +36,11 @@ public:
     int flatten(float* out_xyzi, int cap, int* n_out);
     // re-sort every valid point into fresh, evenly filled leaves (ikd-Tree's Rebuild, ikd_Tree.cpp:736-764)
     int rebuild();
+    // re-list every live slot in the hashed cell directory (map.cuh); done by build / rebuild, and when inserts crowd it
+    int build_directory();
+    void set_cell_directory(bool on, float cell_size) { dir_enabled_ = on; cell_override_ = cell_size; }
+    int dir_rebuild_count() const { return n_dir_rebuilds_; }
+    int dir_stats(int* out6) const;
     // recompute every AABB from the valid points (after deletions)
     int refit();
 
@@ -68,7 +73,11 @@ private:
     int n_valid_ = 0, n_tomb_ = 0, n_rebuilds_ = 0;
     bool built_ = false;
 
-    DeviceBuffer pts_, payload_, next_, counters_;
+    DeviceBuffer pts_, payload_, next_, counters_, dir_tab_, dir_ext_;
+    bool dir_enabled_ = true;
+    float cell_override_ = 0.f;           // 0: cell edge = 2 x downsample size
+    size_t dir_min_cap_ = 0, dir_min_ext_ = 0;
+    int n_dir_rebuilds_ = 0;
     DeviceBuffer ebox_[MAX_LEVELS];
     DeviceBuffer segid_, segtab_[2], bbox_;        // k-d partition build scratch
     DeviceBuffer src_, keys_in_, keys_out_, vals_in_, vals_out_, cub_tmp_, scratch_, scratch2_, scratch3_;

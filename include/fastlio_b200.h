@@ -83,6 +83,13 @@ int fl_map_tree_range(fl_map_t* m, float* box6);
 int fl_map_rebuild(fl_map_t* m);
 /* introspection: [0] main leaves [1] overflow leaves [2] internal levels [3] rebuilds so far */
 int fl_map_stats(fl_map_t* m, int* out4);
+/* The k-NN fast path: a hashed directory of cubic cells over the same points (no reference counterpart; the results are
+ * those of KD_TREE::Nearest_Search either way).  on = 0 answers every query through the BVH walk; cell_size <= 0 picks
+ * 2 x downsample_size.  Takes effect immediately (the directory is re-listed). */
+int fl_map_set_cell_directory(fl_map_t* m, int on, float cell_size);
+/* [0] cells [1] external buckets [2] crowded cells (queries touching them use the BVH walk) [3] table capacity
+ * [4] directory re-lists triggered by inserts [5] queries answered by the BVH walk since the last call (-1: directory off) */
+int fl_map_dir_stats(fl_map_t* m, int* out6);
 
 /* ------------------------------------------------------------------ filter: esekf + h_share_model */
 /* esekf::esekf + esekf::init_dyn_share(f, f_x, f_w, h_share_model, maximum_iteration, limit)

@@ -40,7 +40,7 @@ SYMBOLS = [
     "fl_map_create", "fl_map_destroy", "fl_map_set_downsample", "fl_map_build", "fl_map_size", "fl_map_validnum",
     "fl_map_knn", "fl_map_add_points", "fl_map_delete_boxes", "fl_map_flatten", "fl_map_tree_range",
     "fl_map_rebuild", "fl_map_stats", "fl_map_set_cell_directory", "fl_map_dir_stats",
-    "fl_filter_create", "fl_filter_destroy", "fl_filter_set_params", "fl_filter_set_solver", "fl_filter_set_search", "fl_filter_update",
+    "fl_filter_create", "fl_filter_destroy", "fl_filter_set_params", "fl_filter_set_solver", "fl_filter_set_search", "fl_filter_set_fused", "fl_filter_update",
     "fl_filter_map_incremental", "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
     "fl_filter_upload_state", "fl_filter_run", "fl_filter_download_state", "fl_filter_sync",
     "fl_filter_time_resident", "fl_filter_time_search_pass", "fl_filter_time_e2e", "fl_filter_gpu_launches",
@@ -86,6 +86,7 @@ def load():
     L.fl_filter_set_params.argtypes = [C.c_void_p, C.c_int, _f64p, C.c_int]
     L.fl_filter_set_solver.argtypes = [C.c_void_p, C.c_int]
     L.fl_filter_set_search.argtypes = [C.c_void_p, C.c_int]
+    L.fl_filter_set_fused.argtypes = [C.c_void_p, C.c_int]
     L.fl_filter_update.argtypes = [C.c_void_p, _f32p, C.c_int, _f64p, _f64p, C.c_double, C.POINTER(C.c_double)]
     L.fl_filter_map_incremental.argtypes = [C.c_void_p, C.c_double, C.c_int, _i32p]
     L.fl_filter_get_nearest.argtypes = [C.c_void_p, _f32p, _i32p, C.c_int]
@@ -217,7 +218,7 @@ class Esekf:
     """esekf::update_iterated_dyn_share_modified with the fused device measurement model."""
 
     def __init__(self, tree: KdTree, max_points: int = 100000, max_iter: int = 4, limit: float = 0.001,
-                 extrinsic_est_en: bool = False, solver: int = 1, search: int = -1):
+                 extrinsic_est_en: bool = False, solver: int = 1, search: int = -1, fused: int = -1):
         self._L = load()
         self.tree = tree
         h = C.c_void_p()
@@ -229,6 +230,9 @@ class Esekf:
         _check(self._L.fl_filter_set_solver(self.h, solver))
         if search >= 0:
             _check(self._L.fl_filter_set_search(self.h, search))
+        if fused >= 0:
+            _check(self._L.fl_filter_set_fused(self.h, fused))
+        self._fused = (fused != 0) and solver == 1 and os.environ.get('FASTLIO_B200_LEGACY', '0') != '1'
 
     def close(self):
         if getattr(self, "h", None):
@@ -319,6 +323,9 @@ class Esekf:
 
     def gpu_launches(self) -> int:
         return _check(self._L.fl_filter_gpu_launches(self.h))
+
+    def fused(self) -> bool:
+        return self._fused
 
     def comm_init(self, nranks: int, rank: int, unique_id: bytes):
         _check(self._L.fl_filter_comm_init(self.h, nranks, rank, unique_id))

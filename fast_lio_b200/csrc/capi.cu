@@ -168,6 +168,7 @@ int fl_filter_destroy(fl_filter_t* f) {
 }
 int fl_filter_set_params(fl_filter_t* f, int max_iter, const double* limit23, int extr) { FILTER_GUARD(f); return f->impl->set_params(max_iter, limit23, extr); }
 int fl_filter_set_solver(fl_filter_t* f, int mode) { FILTER_GUARD(f); if (mode < 0 || mode > 1) return FL_ERR_ARG; f->impl->set_solver(mode); return FL_OK; }
+int fl_filter_set_fused(fl_filter_t* f, int on) { FILTER_GUARD(f); f->impl->set_fused(on != 0); return FL_OK; }
 int fl_filter_set_search(fl_filter_t* f, int mode) { FILTER_GUARD(f); if (mode < 0 || mode > 1) return FL_ERR_ARG; f->impl->set_search_mode(mode); return FL_OK; }
 int fl_filter_update(fl_filter_t* f, const float* body, int nq, double* x26, double* P, double R, double* solve_time_s) {
     FILTER_GUARD(f);

@@ -934,6 +934,11 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
         }
         if (threadIdx.x == 0) p2p->epoch = epoch;
         __syncthreads();
+        if (ctl->error == 2) {                  // a peer never delivered: end the update here instead of solving with garbage
+            if (threadIdx.x == 0) { ctl->done = 1; ctl->n_pass = ctl->n_pass + 1; }
+            mirror_result(ctl);
+            return;
+        }
     }
     solve_finish<SOLVER, EXTR>(S, ctl, sc, logs);
     mirror_result(ctl);
@@ -988,6 +993,10 @@ __global__ void k_p2p_barrier(P2PState* p2p) {
     __syncthreads();
     if (threadIdx.x == 0) p2p->bar_epoch = epoch;
 }
+
+}  // namespace fl
+#include "update.cuh"
+namespace fl {
 
 // ============================================================================= map_incremental
 // laserMapping.cpp:427-474: which scan points enter the map, and how.  One thread per point.
@@ -1105,6 +1114,12 @@ int Filter::init() {
     else if (search_occ_ == 5) FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<5>, SEARCH_THREADS, 0));
     else FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<4>, SEARCH_THREADS, 0));
     search_grid_max_ = sms_ * std::max(1, occ);
+    if (const char* e = getenv("FASTLIO_B200_LEGACY")) fused_ = !(e[0] == '1');      // A/B: the split kernels of round 1
+    FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_update<false>, UPD_THREADS, 0));
+    upd_capacity_[0] = sms_ * std::max(1, occ);
+    FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_update<true>, UPD_THREADS, 0));
+    upd_capacity_[1] = sms_ * std::max(1, occ);
+    FL_CHECK(partials_.reserve(sizeof(double) * PSTRIDE * (size_t)std::max(upd_capacity_[0], upd_capacity_[1])));
     max_resid_grid_ = sms_;
     FL_CHECK(partials_.reserve(sizeof(double) * PSTRIDE * (size_t)max_resid_grid_));
     FL_CHECK(reserve(std::max(1, max_points_)));
@@ -1163,9 +1178,12 @@ int Filter::set_shard(int q_begin, int q_end) {
 
 int Filter::upload_state(const double* x26, const double* P, double R, bool snapshot) {
     FL_CUDA(cudaSetDevice(map_->device()));
+    // h_ctl_ is the source of the upload below AND the block the device mirrors its result into: nothing queued earlier
+    // on the stream may still be reading or writing it when it is rewritten
+    FL_CUDA(cudaStreamSynchronize(stream()));
     // what update_iterated_dyn_share_modified sets up before its loop (esekfom.hpp:1621-1631)
     FilterCtl& c = *h_ctl_;
-    c.iter = -1; c.t = 0; c.converge = 1; c.done = 0; c.n_pass = 0; c.error = 0; c.ticket = 0; c.pad_ = 0;
+    c.iter = -1; c.t = 0; c.converge = 1; c.done = 0; c.n_pass = 0; c.error = 0; c.ticket = 0; c.gen = 0;
     c.max_iter = max_iter_;
     c.host_mirror = (mirror_ && !snapshot) ? h_ctl_ : nullptr;      // whole-update calls only: resident pipelines fetch the result when they want it
     c.extrinsic_est = extrinsic_est_;
@@ -1191,6 +1209,24 @@ int Filter::run_passes() {
     FL_CUDA(cudaSetDevice(map_->device()));
     if (scan_.q_end > scan_.Q) { set_last_error("shard exceeds the scan"); return FL_ERR_ARG; }
     launches_ = 0;
+    if (fused()) {
+        cudaStream_t st = stream();
+        if (nranks_ > 1 && !p2p_on_) {
+            // NCCL between the measurement and the solve: one pass per launch pair
+            for (int pass = 0; pass <= max_iter_; pass++) {
+                FL_CHECK(launch_update(1, 1, 0));
+                int rc = nccl_->AllReduce(red_.ptr, red_.ptr, NRED, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm_, st);
+                if (rc != 0) { set_last_error("ncclAllReduce failed: %d", rc); return FL_ERR_NCCL; }
+                FL_CHECK(launch_update(1, 3, 0));
+                launches_ += 2;
+            }
+        } else {
+            FL_CHECK(launch_update(max_iter_ + 1, nranks_ > 1 ? 2 : 0, 0));
+            launches_ = 1;
+        }
+        FL_CUDA(cudaGetLastError());
+        return FL_OK;
+    }
     for (int pass = 0; pass <= max_iter_; pass++) {
         FL_CHECK(launch_search_only());
         FL_CHECK(launch_residual_only());
@@ -1221,9 +1257,28 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cud
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// the fused persistent kernel: blockIdx 0 solves, the others measure; every block must be co-resident (they wait for each other)
+int Filter::launch_update(int max_passes, int mode, int search_only) {
+    FL_CUDA(cudaSetDevice(map_->device()));
+    const int nq = scan_.q_end - scan_.q_begin;
+    UpdArgs a;
+    a.m = map_->view();
+    if (search_mode_ == 0) a.m.dir.cap = 0;                  // A/B: every query through the BVH walk
+    a.sc = scan_; a.ctl = ctl_.as<FilterCtl>(); a.partials = partials_.as<double>(); a.red_g = red_.as<double>();
+    a.logs = logs_.as<PassLog>(); a.p2p = p2p_.as<P2PState>();
+    a.mode = mode; a.max_passes = max_passes; a.search_only = search_only;
+    const int cap = upd_capacity_[extrinsic_est_ ? 1 : 0];
+    int workers = mode == 3 ? 0 : std::min(cap - 1, (nq + UPD_THREADS - 1) / UPD_THREADS);
+    if (workers < 0) workers = 0;
+    if (extrinsic_est_) FL_CUDA(launch_pdl(k_update<true>, workers + 1, UPD_THREADS, stream(), pdl_, a));
+    else FL_CUDA(launch_pdl(k_update<false>, workers + 1, UPD_THREADS, stream(), pdl_, a));
+    return FL_OK;
+}
+
 int Filter::launch_search_only() {
     FL_CUDA(cudaSetDevice(map_->device()));
     const int nq = scan_.q_end - scan_.q_begin;
+    if (fused()) return launch_update(1, 0, 1);
     if (search_mode_ == 1) {
         const int tgrid = std::max(1, (nq + SEARCH_C_THREADS - 1) / SEARCH_C_THREADS);
         FL_CUDA(launch_pdl(k_search_c, tgrid, SEARCH_C_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
@@ -1268,7 +1323,12 @@ int Filter::download_state(double* x26, double* P, int* n_pass) {
         FL_CUDA(cudaMemcpyAsync(h_ctl_, ctl_.ptr, offsetof(FilterCtl, P_prop), cudaMemcpyDeviceToHost, stream()));
         FL_CUDA(cudaStreamSynchronize(stream()));
     }
-    if (h_ctl_->error) { set_last_error("update: singular system on device"); return FL_ERR_STATE; }
+    if (h_ctl_->error) {
+        const int e = h_ctl_->error;
+        set_last_error(e == 2 ? "update: a peer rank never delivered its sums (peer-memory exchange timed out)"
+                              : (e == 3 ? "update: a block gave up waiting for the solver / the workers on the device" : "update: singular system on device"));
+        return e == 2 ? FL_ERR_NCCL : FL_ERR_STATE;
+    }
     if (x26) memcpy(x26, h_ctl_->x, sizeof(double) * XLEN);
     if (P) memcpy(P, h_ctl_->P, sizeof(double) * NDOF * NDOF);
     if (n_pass) *n_pass = h_ctl_->n_pass;

@@ -27,9 +27,9 @@ struct FilterCtl {
     int n_pass;          // passes executed so far
     int max_iter;        // maximum_iter
     int extrinsic_est;   // extrinsic_est_en (laserMapping.cpp:739)
-    int error;           // device-side failure (singular system)
+    int error;           // device-side failure: 1 singular system, 2 a peer never delivered its sums, 3 a block gave up waiting
     int ticket;          // k_residual: blocks finished so far (the last one reduces and solves)
-    int pad_;
+    int gen;             // k_update: passes published so far (the workers of the next pass spin on it)
     double R;            // LASER_POINT_COV passed as R
     double limit[NDOF];
     double x[XLEN];
@@ -104,6 +104,10 @@ public:
     int p2p_connect(int nranks, int rank, const void* handles64);
     int p2p_barrier();                                 // device-side rendezvous of all ranks on the stream (no-op on one rank)
 
+    // 1 (default): the whole update in one persistent fused kernel (k_update, update.cuh); 0: the two-kernels-per-pass chain
+    // (k_search / k_search_c + k_residual) it grew out of, kept for A/B and for solver mode 0
+    void set_fused(bool on) { fused_ = on; }
+    bool fused() const { return fused_ && solver_ == 1; }
     int gpu_launches() const { return launches_; }
     const long long* host_ns() const { return host_ns_; }
     const float4* nearest_device() const { return scan_.nearest; }
@@ -131,6 +135,9 @@ private:
     FilterCtl* h_ctl_ = nullptr;       // pinned staging
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int sms_ = 0, search_grid_max_ = 0, max_resid_grid_ = 0, resid_grid_ = 1;
+    bool fused_ = true;
+    int upd_capacity_[2] = {0, 0};     // co-resident k_update<EXTR> blocks on this device
+    int launch_update(int max_passes, int mode, int search_only);
     int launches_ = 0;
     long long host_ns_[4] = {0, 0, 0, 0};
     bool shard_set_ = false;

@@ -317,69 +317,122 @@ static __constant__ signed char CELL_ORDER[27][4] = {
     {0, -1, -1, 0}, {0, -1, 1, 0}, {0, 1, -1, 0}, {0, 1, 1, 0},
     {-1, -1, -1, 0}, {-1, -1, 1, 0}, {-1, 1, -1, 0}, {-1, 1, 1, 0}, {1, -1, -1, 0}, {1, -1, 1, 0}, {1, 1, -1, 0}, {1, 1, 1, 0}};
 
-__device__ __forceinline__ void cell_consider(const MapView& m, int idx, int cx, int cy, int cz, float qx, float qy, float qz, TBest& kb) {
-    const float4 p = __ldg(&m.pts[idx]);
-    const float inv = m.dir.inv_cell;
-    // the slot must still hold a live point of THIS cell (deleted points keep their entry; re-used slots leave stale ones)
+__host__ __device__ constexpr int cell_off(int t, int axis) {
+    // own cell, 6 faces, 12 edges, 8 corners -- the same order as CELL_ORDER
+    constexpr signed char T[27][3] = {
+        {0, 0, 0},
+        {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+        {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1},
+        {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
+        {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
+    return T[t][axis];
+}
+
+// one candidate: the slot must still hold a live point of THIS cell (deleted points keep their entry; re-used slots leave stale ones)
+__device__ __forceinline__ void cell_consider(const float4& p, int idx, float inv, int cx, int cy, int cz, float qx, float qy, float qz, TBest& kb) {
     if (slot_valid(p) && cell_coord(p.x, inv) == cx && cell_coord(p.y, inv) == cy && cell_coord(p.z, inv) == cz) {
         const float dd = sq_dist3(qx, qy, qz, p.x, p.y, p.z);
         if (dd < kb.d[KNN_K - 1]) kb.insert(dd, idx);
     }
 }
 
-// scan one cell; sets `crowded` when the cell lists more points than the directory holds
-__device__ __forceinline__ void cell_scan(const MapView& m, int cx, int cy, int cz, float qx, float qy, float qz, TBest& kb, bool& crowded) {
-    const CellDir& D = m.dir;
-    const unsigned long long key = cell_key(cx, cy, cz);
-    unsigned s = cell_slot(key, D.cap);
-    const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
-    uint4 a;
-    unsigned probes = 0;
-    while (true) {
-        a = __ldg(&tab[2 * (size_t)s]);
-        const unsigned long long k = (unsigned long long)a.x | ((unsigned long long)a.y << 32);
-        if (k == key) break;
-        if (k == 0ull) return;
-        if (++probes >= D.cap) { crowded = true; return; }          // cannot happen (load factor < 0.7); never spin
-        s = (s + 1 == D.cap) ? 0u : s + 1;
-    }
-    const int cnt = (int)a.w;
-    if (cnt > CELL_MAX || (cnt > CELL_INLINE && a.z == 0u)) { crowded = true; return; }
-    const uint4 b = __ldg(&tab[2 * (size_t)s + 1]);
-    if (cnt > 0) cell_consider(m, (int)b.x, cx, cy, cz, qx, qy, qz, kb);
-    if (cnt > 1) cell_consider(m, (int)b.y, cx, cy, cz, qx, qy, qz, kb);
-    if (cnt > 2) cell_consider(m, (int)b.z, cx, cy, cz, qx, qy, qz, kb);
-    if (cnt > 3) cell_consider(m, (int)b.w, cx, cy, cz, qx, qy, qz, kb);
-    if (cnt > CELL_INLINE) {
-        const int* ext = D.ext + (size_t)((int)a.z - 1) * CELL_EXT;
-#pragma unroll 1
-        for (int j = 0; j < cnt - CELL_INLINE; j++) cell_consider(m, __ldg(&ext[j]), cx, cy, cz, qx, qy, qz, kb);
-    }
-}
-
 // k-NN of one query by one thread.  Returns true when kb is PROVEN to be the exact answer.
+// Two phases, arranged for memory-level parallelism (a scan is only a few warps per SM, so the chain of dependent
+// loads of one thread IS the run time):  1. the keys of all 27 cells are probed with independent loads (which also
+// brings their directory entries into L1);  2. only the cells that exist and can still matter are visited, nearest
+// first, each with its (up to four inline) point loads issued together.
 __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, float qz, TBest& kb) {
     const CellDir& D = m.dir;
     kb.init();
     if (D.cap == 0u) return false;
-    const int ix = cell_coord(qx, D.inv_cell), iy = cell_coord(qy, D.inv_cell), iz = cell_coord(qz, D.inv_cell);
+    const float inv = D.inv_cell;
+    const int ix = cell_coord(qx, inv), iy = cell_coord(qy, inv), iz = cell_coord(qz, inv);
     if (abs(ix) >= CELL_CLAMP - 1 || abs(iy) >= CELL_CLAMP - 1 || abs(iz) >= CELL_CLAMP - 1) return false;
+    const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
+    // ---- phase 1: which of the 27 cells exist?  bit t of `hit`: key found at its home slot; of `coll`: home slot taken by another cell
+    unsigned hit = 0u, coll = 0u;
+    {
+        unsigned long long got[27];
+#pragma unroll
+        for (int t = 0; t < 27; t++) {
+            const unsigned long long key = cell_key(ix + cell_off(t, 0), iy + cell_off(t, 1), iz + cell_off(t, 2));
+            got[t] = __ldg(reinterpret_cast<const unsigned long long*>(&tab[2 * (size_t)cell_slot(key, D.cap)])) ^ key;
+        }
+#pragma unroll
+        for (int t = 0; t < 27; t++) {
+            const unsigned long long key = cell_key(ix + cell_off(t, 0), iy + cell_off(t, 1), iz + cell_off(t, 2));
+            if (got[t] == 0ull) hit |= 1u << t;
+            else if (got[t] != key) coll |= 1u << t;           // (stored ^ key) == key  <=>  stored == 0: free slot, the cell does not exist
+        }
+    }
     const float c = D.cell;
     // distance from the query to the low / high face of its own cell, shrunk by more than any rounding of the cell arithmetic
     const float marg = 4e-6f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 2.f * c);
     const float lox = fmaxf(qx - (float)ix * c - marg, 0.f), hix = fmaxf((float)(ix + 1) * c - qx - marg, 0.f);
     const float loy = fmaxf(qy - (float)iy * c - marg, 0.f), hiy = fmaxf((float)(iy + 1) * c - qy - marg, 0.f);
     const float loz = fmaxf(qz - (float)iz * c - marg, 0.f), hiz = fmaxf((float)(iz + 1) * c - qz - marg, 0.f);
+    // ---- phase 2
     bool crowded = false;
+    unsigned todo = hit | coll;
 #pragma unroll 1
-    for (int t = 0; t < 27; t++) {
+    while (todo) {
+        const int t = __ffs(todo) - 1;
+        todo &= todo - 1;
         const int dx = CELL_ORDER[t][0], dy = CELL_ORDER[t][1], dz = CELL_ORDER[t][2];
         const float gx = dx < 0 ? lox : (dx > 0 ? hix : 0.f);
         const float gy = dy < 0 ? loy : (dy > 0 ? hiy : 0.f);
         const float gz = dz < 0 ? loz : (dz > 0 ? hiz : 0.f);
-        if (gx * gx + gy * gy + gz * gz < kb.d[KNN_K - 1]) cell_scan(m, ix + dx, iy + dy, iz + dz, qx, qy, qz, kb, crowded);
+        if (!(gx * gx + gy * gy + gz * gz < kb.d[KNN_K - 1])) continue;      // its nearest face is not closer than the k-th best
+        const int cx = ix + dx, cy = iy + dy, cz = iz + dz;
+        const unsigned long long key = cell_key(cx, cy, cz);
+        unsigned s = cell_slot(key, D.cap);
+        uint4 a = __ldg(&tab[2 * (size_t)s]);
+        if ((coll >> t) & 1u) {                                              // rare: walk the probe sequence
+            bool found = false;
+            for (unsigned probes = 0; probes < D.cap; probes++) {
+                const unsigned long long k = (unsigned long long)a.x | ((unsigned long long)a.y << 32);
+                if (k == key) { found = true; break; }
+                if (k == 0ull) break;
+                s = (s + 1 == D.cap) ? 0u : s + 1;
+                a = __ldg(&tab[2 * (size_t)s]);
+            }
+            if (!found) continue;
+        }
+        const int cnt = (int)a.w;
+        if (cnt > CELL_MAX || (cnt > CELL_INLINE && a.z == 0u)) { crowded = true; break; }
+        const uint4 b = __ldg(&tab[2 * (size_t)s + 1]);
+        // the inline points, loads first
+        const int i0 = (int)b.x, i1 = (int)b.y, i2 = (int)b.z, i3 = (int)b.w;
+        float4 p0, p1, p2, p3;
+        p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);               // flag 0: not a live point
+        if (cnt > 0) p0 = __ldg(&m.pts[i0]);
+        if (cnt > 1) p1 = __ldg(&m.pts[i1]);
+        if (cnt > 2) p2 = __ldg(&m.pts[i2]);
+        if (cnt > 3) p3 = __ldg(&m.pts[i3]);
+        cell_consider(p0, i0, inv, cx, cy, cz, qx, qy, qz, kb);
+        cell_consider(p1, i1, inv, cx, cy, cz, qx, qy, qz, kb);
+        cell_consider(p2, i2, inv, cx, cy, cz, qx, qy, qz, kb);
+        cell_consider(p3, i3, inv, cx, cy, cz, qx, qy, qz, kb);
+        if (cnt > CELL_INLINE) {
+            const int* ext = D.ext + (size_t)((int)a.z - 1) * CELL_EXT;
+#pragma unroll 1
+            for (int j = 0; j < cnt - CELL_INLINE; j += 4) {
+                const int4 e = __ldg(reinterpret_cast<const int4*>(ext + j));
+                const int n4 = cnt - CELL_INLINE - j;
+                p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n4 > 0) p0 = __ldg(&m.pts[e.x]);
+                if (n4 > 1) p1 = __ldg(&m.pts[e.y]);
+                if (n4 > 2) p2 = __ldg(&m.pts[e.z]);
+                if (n4 > 3) p3 = __ldg(&m.pts[e.w]);
+                cell_consider(p0, e.x, inv, cx, cy, cz, qx, qy, qz, kb);
+                cell_consider(p1, e.y, inv, cx, cy, cz, qx, qy, qz, kb);
+                cell_consider(p2, e.z, inv, cx, cy, cz, qx, qy, qz, kb);
+                cell_consider(p3, e.w, inv, cx, cy, cz, qx, qy, qz, kb);
+            }
+        }
     }
     if (crowded || kb.idx[KNN_K - 1] < 0) return false;
+    // proof: every point outside the 3x3x3 block is at least g away
     const float g = fminf(fminf(fminf(lox, hix), fminf(loy, hiy)), fminf(loz, hiz)) + c - marg;
     return kb.d[KNN_K - 1] < g * g;
 }

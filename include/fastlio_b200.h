@@ -102,9 +102,12 @@ int fl_filter_set_params(fl_filter_t* f, int max_iter, const double* limit23, in
  *    algebraically identical;
  * 0: the information form with two 23x23 inversions exactly as written in the reference (validation) */
 int fl_filter_set_solver(fl_filter_t* f, int mode);
-/* kNN kernel of the search passes: 0 (default) one warp per scan point; 1 one thread per scan point -- same
- * results, kept for comparison (2.8x slower on B200: fully divergent 16-byte loads saturate the L1 wavefront rate) */
+/* kNN of the search passes: 1 (default) one lane per scan point through the map's cell directory, the BVH walk for
+ * whatever that cannot prove; 0 one warp per scan point through the BVH walk only -- same neighbours, same distances */
 int fl_filter_set_search(fl_filter_t* f, int mode);
+/* 1 (default): the whole update in ONE persistent kernel launch (h_share_model fused with the search, the Kalman step
+ * in the kernel's solver block); 0: the two-kernels-per-pass chain it grew out of (A/B; solver mode 0 always uses it) */
+int fl_filter_set_fused(fl_filter_t* f, int on);
 /* esekf::update_iterated_dyn_share_modified(R, solve_time) with feats_down_body bound
  *                                                                   esekfom.hpp:1619-1931, laserMapping.cpp:638-754, :960
  * x26 / P: in = kf.get_x()/get_P() before the update, out = after.  solve_time_s (may be NULL)

@@ -148,6 +148,31 @@ def test_no_effective_points_leaves_state_untouched(problems):
     assert all(l["valid"] == 0 and l["effct"] == 0 for l in logs)
 
 
+@pytest.mark.parametrize("extr", [0, 1])
+def test_fused_kernel_equals_the_split_kernels(problems, extr):
+    """k_update (one persistent launch, solver block with the one-right-hand-side gain) against the two-kernels-per-pass chain
+    with the 6x6 / 12x12 solve it replaced: same per-pass sums bit for bit (same rows, same reduction order is NOT required --
+    the block partition differs -- so 1e-12), same state to rounding."""
+    pr = problems("small")
+    t = api.KdTree(0, 0.5); t.Build(pr.map_pts)
+    res = []
+    for fused in (1, 0):
+        f = api.Esekf(t, max_points=len(pr.scan), max_iter=pr.cfg.max_iter, extrinsic_est_en=bool(extr), fused=fused)
+        assert f.fused() == bool(fused)
+        x, P, _ = f.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
+        res.append((x, P, f.pass_logs(), f.nearest(len(pr.scan)), f.selected(len(pr.scan)), f.gpu_launches()))
+    (xa, Pa, la, na, sa, launches_a), (xb, Pb, lb, nb, sb, launches_b) = res
+    assert launches_a == 1 and launches_b >= 8
+    assert len(la) == len(lb)
+    for a, b in zip(la, lb):
+        assert (a["searched"], a["effct"], a["converged"], a["valid"]) == (b["searched"], b["effct"], b["converged"], b["valid"])
+        assert np.allclose(a["HtH"], b["HtH"], rtol=1e-12, atol=1e-12 * np.abs(b["HtH"]).max())
+        assert np.abs(a["x_after"] - b["x_after"]).max() < 1e-11
+    assert np.array_equal(na[0], nb[0]) and np.array_equal(na[1], nb[1]) and np.array_equal(sa, sb)
+    assert np.abs(xa - xb).max() < 1e-11
+    assert np.abs(Pa - Pb).max() <= 1e-9 * np.abs(Pb).max()
+
+
 def test_update_is_deterministic(problems):
     pr = problems("small")
     t = api.KdTree(0, 0.5); t.Build(pr.map_pts)

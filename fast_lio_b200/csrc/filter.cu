@@ -1084,7 +1084,7 @@ Filter::~Filter() {
     for (int r = 0; r < P2P_MAX_RANKS; r++) if (peer_ptr_[r]) cudaIpcCloseMemHandle(peer_ptr_[r]);
     mailbox_.release(); p2p_.release();
     body_.release(); nearest_.release(); nearest_cnt_.release(); selected_.release(); normvec_.release(); plane_.release();
-    partials_.release(); red_.release(); ctl_.release(); ctl0_.release(); logs_.release();
+    partials_.release(); red_.release(); ctl_.release(); ctl0_.release(); logs_.release(); pub_.release();
     mi_world_.release(); mi_flag_add_.release(); mi_flag_no_.release(); mi_list_add_.release(); mi_list_no_.release(); mi_tmp_.release(); mi_counts_.release();
     if (h_ctl_) cudaFreeHost(h_ctl_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -1100,6 +1100,8 @@ int Filter::init() {
     FL_CHECK(ctl0_.reserve(sizeof(FilterCtl)));
     FL_CHECK(red_.reserve(sizeof(double) * PSTRIDE));
     FL_CHECK(logs_.reserve(sizeof(PassLog) * MAX_LOGS));
+    FL_CHECK(pub_.reserve(512));
+    FL_CUDA(cudaMemsetAsync(pub_.ptr, 0, 512, stream()));
     FL_CUDA(cudaMallocHost(&h_ctl_, sizeof(FilterCtl)));
     memset(h_ctl_, 0, sizeof(FilterCtl));
     FL_CUDA(cudaMemsetAsync(ctl_.ptr, 0, sizeof(FilterCtl), stream()));
@@ -1267,6 +1269,7 @@ int Filter::launch_update(int max_passes, int mode, int search_only) {
     a.sc = scan_; a.ctl = ctl_.as<FilterCtl>(); a.partials = partials_.as<double>(); a.red_g = red_.as<double>();
     a.logs = logs_.as<PassLog>(); a.p2p = p2p_.as<P2PState>();
     a.mode = mode; a.max_passes = max_passes; a.search_only = search_only;
+    a.pub = pub_.as<unsigned long long>(); a.nonce = ++launch_nonce_;
     const int cap = upd_capacity_[extrinsic_est_ ? 1 : 0];
     int workers = mode == 3 ? 0 : std::min(cap - 1, (nq + UPD_THREADS - 1) / UPD_THREADS);
     if (workers < 0) workers = 0;

@@ -136,6 +136,8 @@ private:
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int sms_ = 0, search_grid_max_ = 0, max_resid_grid_ = 0, resid_grid_ = 1;
     bool fused_ = true;
+    DeviceBuffer pub_;                 // k_update's publication block
+    unsigned launch_nonce_ = 0;
     int upd_capacity_[2] = {0, 0};     // co-resident k_update<EXTR> blocks on this device
     int launch_update(int max_passes, int mode, int search_only);
     int launches_ = 0;

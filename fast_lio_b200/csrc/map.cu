@@ -284,25 +284,16 @@ __global__ void k_dir_fill(MapView m, int n_leaf_used) {
 // incremental: one thread (lane 0 of the inserting warp) lists a freshly written slot under its cell
 __device__ __forceinline__ void dir_add(const MapView& m, const float4& p, int slot, int* counters) {
     const CellDir& D = m.dir;
-    if (D.cap == 0u) return;
     const unsigned e = dir_claim(D, point_cell_key(D, p), counters);
     if (e == 0xffffffffu) return;
     CellEntry& E = D.tab[e];
-    // a slot that is being re-used may still be listed under this very cell: never list it twice
-    const int seen = min(atomicAdd(&E.cnt, 0), CELL_MAX);
-    for (int j = 0; j < seen; j++) {
-        int v;
-        if (j < CELL_INLINE) v = *(volatile int*)&E.idx[j];
-        else { const int x = *(volatile int*)&E.ext; v = x > 0 ? *(volatile int*)&D.ext[(size_t)(x - 1) * CELL_EXT + j - CELL_INLINE] : -1; }
-        if (v == slot) return;
-    }
     const int pos = atomicAdd(&E.cnt, 1);
     if (pos < CELL_INLINE) { *(volatile int*)&E.idx[pos] = slot; return; }
     if (pos >= CELL_MAX) { if (pos == CELL_MAX) atomicAdd(&counters[C_DIR_CROWDED], 1); return; }
     int x;
     if (pos == CELL_INLINE) {                   // the fifth point of the cell brings the external bucket
         x = dir_alloc_ext(D, counters) + 1;
-        if (x <= 0) return;                     // pool exhausted: the host grows the pool and rebuilds the directory
+        if (x <= 0) return;                     // pool exhausted: the host grows the pool and re-lists the directory
         atomicExch(&E.ext, x);
     } else {
         const long long t0 = clock64();
@@ -311,6 +302,34 @@ __device__ __forceinline__ void dir_add(const MapView& m, const float4& p, int s
         }
     }
     *(volatile int*)&D.ext[(size_t)(x - 1) * CELL_EXT + pos - CELL_INLINE] = slot;
+}
+// A slot is listed exactly once, under the cell of the point it holds.  When an insert re-uses the slot of a deleted point
+// (a tombstone keeps its listing: the search skips it by its flag), the listing stays if the new point falls into the same
+// cell; otherwise the old one is struck out (-1, skipped by the search, re-packed by the next re-list) and a new one added.
+__device__ __forceinline__ void dir_move(const MapView& m, bool was_tomb, const float4& old_p, const float4& p, int slot, int* counters) {
+    const CellDir& D = m.dir;
+    if (D.cap == 0u) return;
+    if (was_tomb) {
+        const unsigned long long ok = point_cell_key(D, old_p);
+        if (ok == point_cell_key(D, p)) return;
+        unsigned s = cell_slot(ok, D.cap);
+        for (unsigned probes = 0; probes < D.cap; probes++) {
+            const unsigned long long k = *(volatile unsigned long long*)&D.tab[s].key;
+            if (k == ok) {
+                CellEntry& E = D.tab[s];
+                const int seen = min(atomicAdd(&E.cnt, 0), CELL_MAX);
+                const int x = atomicAdd(&E.ext, 0);
+                for (int j = 0; j < seen; j++) {
+                    volatile int* at = j < CELL_INLINE ? (volatile int*)&E.idx[j] : (x > 0 ? (volatile int*)&D.ext[(size_t)(x - 1) * CELL_EXT + j - CELL_INLINE] : nullptr);
+                    if (at && *at == slot) { *at = -1; break; }
+                }
+                break;
+            }
+            if (k == 0ull) break;
+            s = (s + 1 == D.cap) ? 0u : s + 1;
+        }
+    }
+    dir_add(m, p, slot, counters);
 }
 
 // Batched Nearest_Search: one lane per query (cell directory), BVH walk for what that cannot prove.
@@ -349,7 +368,7 @@ __global__ void k_delete_boxes(MapView m, const float* __restrict__ boxes, int n
         if (slot_valid(p)) {
             bool hit = false;
             for (int b = 0; b < nb && !hit; b++) hit = in_box(p, &boxes[b * 6], &boxes[b * 6 + 3]);
-            if (hit) { m.pts[slot].w = __int_as_float(0); local++; }
+            if (hit) { m.pts[slot].w = __int_as_float(SLOT_TOMB); local++; }
         }
     }
 #pragma unroll
@@ -444,7 +463,7 @@ struct BoxKill {       // pass 2: invalidate every valid point inside the voxel 
         while (l >= 0) {
             const int slot = l * LEAF + lane;
             const float4 p = m.pts[slot];
-            if (slot_valid(p) && in_box(p, vb.bmin, vb.bmax) && slot != keep) m.pts[slot].w = __int_as_float(0);
+            if (slot_valid(p) && in_box(p, vb.bmin, vb.bmax) && slot != keep) m.pts[slot].w = __int_as_float(SLOT_TOMB);
             l = m.next[l];
         }
     }
@@ -540,18 +559,22 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
         int leaf = home;
         bool placed = false;
         while (!placed) {
-            const int w = __float_as_int(m.pts[leaf * LEAF + lane].w);
-            unsigned freem = __ballot_sync(FULL, w == 0);
+            const float4 cur = m.pts[leaf * LEAF + lane];
+            const int w = __float_as_int(cur.w);
+            unsigned freem = __ballot_sync(FULL, w == SLOT_FREE || w == SLOT_TOMB);
             while (freem && !placed) {
                 const int s = __ffs(freem) - 1;
+                // what lane s saw in the slot: a tombstone still carries the deleted point (and its directory listing)
+                const int seen = __shfl_sync(FULL, w, s);
+                const float ox = __shfl_sync(FULL, cur.x, s), oy = __shfl_sync(FULL, cur.y, s), oz = __shfl_sync(FULL, cur.z, s);
                 int old = 0;
-                if (lane == 0) old = atomicCAS((int*)&m.pts[leaf * LEAF + s].w, 0, 2);
+                if (lane == 0) old = atomicCAS((int*)&m.pts[leaf * LEAF + s].w, seen, SLOT_BUSY);
                 old = __shfl_sync(FULL, old, 0);
-                if (old == 0) {
+                if (old == seen) {
                     if (lane == 0) {
                         m.payload[leaf * LEAF + s] = p.w;
-                        m.pts[leaf * LEAF + s] = make_float4(p.x, p.y, p.z, __int_as_float(1));
-                        dir_add(m, p, leaf * LEAF + s, counters);
+                        m.pts[leaf * LEAF + s] = make_float4(p.x, p.y, p.z, __int_as_float(SLOT_VALID));
+                        dir_move(m, seen == SLOT_TOMB, make_float4(ox, oy, oz, 0.f), p, leaf * LEAF + s, counters);
                     }
                     placed = true;
                 } else {

@@ -65,7 +65,9 @@ struct MapView {
     int leaf_cap;                    // allocated leaves (main + overflow pool)
 };
 
-__device__ __forceinline__ bool slot_valid(const float4& p) { return __float_as_int(p.w) == 1; }
+// slot flag (bits of pts[].w): never used / being written by an insert / live point / deleted point (still listed in the cell directory)
+constexpr int SLOT_FREE = 0, SLOT_VALID = 1, SLOT_BUSY = 2, SLOT_TOMB = 3;
+__device__ __forceinline__ bool slot_valid(const float4& p) { return __float_as_int(p.w) == SLOT_VALID; }
 
 // ----------------------------------------------------------------------------- k-best list
 // Lane j < K holds the j-th best (distance, slot); other lanes hold +inf.  Mirrors MANUAL_HEAP
@@ -328,19 +330,21 @@ __host__ __device__ constexpr int cell_off(int t, int axis) {
     return T[t][axis];
 }
 
-// one candidate: the slot must still hold a live point of THIS cell (deleted points keep their entry; re-used slots leave stale ones)
-__device__ __forceinline__ void cell_consider(const float4& p, int idx, float inv, int cx, int cy, int cz, float qx, float qy, float qz, TBest& kb) {
-    if (slot_valid(p) && cell_coord(p.x, inv) == cx && cell_coord(p.y, inv) == cy && cell_coord(p.z, inv) == cz) {
+// one candidate (a deleted point keeps its listing: it is skipped by its flag; struck-out listings arrive as all-zero points)
+__device__ __forceinline__ void cell_consider(const float4& p, int idx, float qx, float qy, float qz, TBest& kb) {
+    if (slot_valid(p)) {
         const float dd = sq_dist3(qx, qy, qz, p.x, p.y, p.z);
         if (dd < kb.d[KNN_K - 1]) kb.insert(dd, idx);
     }
 }
 
 // k-NN of one query by one thread.  Returns true when kb is PROVEN to be the exact answer.
-// Two phases, arranged for memory-level parallelism (a scan is only a few warps per SM, so the chain of dependent
-// loads of one thread IS the run time):  1. the keys of all 27 cells are probed with independent loads (which also
-// brings their directory entries into L1);  2. only the cells that exist and can still matter are visited, nearest
-// first, each with its (up to four inline) point loads issued together.
+// A scan is only a few warps per SM, so a thread's own instruction and load chain IS the run time:
+//   phase 1  the keys of all 27 cells are probed with independent loads (hashes derived from the own cell's by constant
+//            offsets -- the hash is linear in the cell coordinates); this also brings the entries into L1;
+//   phase 2  only cells that exist and can still matter are visited, nearest first; a lane skips the cells it can prune
+//            BEFORE it joins the loop body, so that the lanes of a warp stay together; the (up to four inline) point loads
+//            of a cell are issued together.
 __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, float qz, TBest& kb) {
     const CellDir& D = m.dir;
     kb.init();
@@ -349,20 +353,26 @@ __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, f
     const int ix = cell_coord(qx, inv), iy = cell_coord(qy, inv), iz = cell_coord(qz, inv);
     if (abs(ix) >= CELL_CLAMP - 1 || abs(iy) >= CELL_CLAMP - 1 || abs(iz) >= CELL_CLAMP - 1) return false;
     const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
-    // ---- phase 1: which of the 27 cells exist?  bit t of `hit`: key found at its home slot; of `coll`: home slot taken by another cell
+    const unsigned long long key0 = cell_key(ix, iy, iz);
+    constexpr unsigned long long G = 0x9E3779B97F4A7C15ull;
+    const unsigned long long h0 = key0 * G;
+    // ---- phase 1: bit t of `hit`: key found at its home slot; of `coll`: home slot taken by another cell
     unsigned hit = 0u, coll = 0u;
     {
         unsigned long long got[27];
 #pragma unroll
         for (int t = 0; t < 27; t++) {
-            const unsigned long long key = cell_key(ix + cell_off(t, 0), iy + cell_off(t, 1), iz + cell_off(t, 2));
-            got[t] = __ldg(reinterpret_cast<const unsigned long long*>(&tab[2 * (size_t)cell_slot(key, D.cap)])) ^ key;
+            // key(t) = key0 + dx 2^42 + dy 2^21 + dz  (no carries: every field stays inside its 21 bits), h = key * G mod 2^64
+            const long long dk = ((long long)cell_off(t, 0) << 42) + ((long long)cell_off(t, 1) << 21) + (long long)cell_off(t, 2);
+            const unsigned long long h = h0 + (unsigned long long)dk * G;
+            const unsigned slot = __umulhi((unsigned)(h >> 32) ^ (unsigned)h, D.cap);
+            got[t] = __ldg(reinterpret_cast<const unsigned long long*>(&tab[2 * (size_t)slot])) ^ (key0 + (unsigned long long)dk);
         }
 #pragma unroll
         for (int t = 0; t < 27; t++) {
-            const unsigned long long key = cell_key(ix + cell_off(t, 0), iy + cell_off(t, 1), iz + cell_off(t, 2));
+            const long long dk = ((long long)cell_off(t, 0) << 42) + ((long long)cell_off(t, 1) << 21) + (long long)cell_off(t, 2);
             if (got[t] == 0ull) hit |= 1u << t;
-            else if (got[t] != key) coll |= 1u << t;           // (stored ^ key) == key  <=>  stored == 0: free slot, the cell does not exist
+            else if (got[t] != key0 + (unsigned long long)dk) coll |= 1u << t;      // (stored ^ key) == key  <=>  free slot: no such cell
         }
     }
     const float c = D.cell;
@@ -375,14 +385,19 @@ __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, f
     bool crowded = false;
     unsigned todo = hit | coll;
 #pragma unroll 1
-    while (todo) {
-        const int t = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int dx = CELL_ORDER[t][0], dy = CELL_ORDER[t][1], dz = CELL_ORDER[t][2];
-        const float gx = dx < 0 ? lox : (dx > 0 ? hix : 0.f);
-        const float gy = dy < 0 ? loy : (dy > 0 ? hiy : 0.f);
-        const float gz = dz < 0 ? loz : (dz > 0 ? hiz : 0.f);
-        if (!(gx * gx + gy * gy + gz * gz < kb.d[KNN_K - 1])) continue;      // its nearest face is not closer than the k-th best
+    while (true) {
+        // next cell of this lane whose nearest face is closer than the k-th best so far
+        int t = -1, dx = 0, dy = 0, dz = 0;
+        while (todo) {
+            const int u = __ffs(todo) - 1;
+            todo &= todo - 1;
+            dx = CELL_ORDER[u][0]; dy = CELL_ORDER[u][1]; dz = CELL_ORDER[u][2];
+            const float gx = dx < 0 ? lox : (dx > 0 ? hix : 0.f);
+            const float gy = dy < 0 ? loy : (dy > 0 ? hiy : 0.f);
+            const float gz = dz < 0 ? loz : (dz > 0 ? hiz : 0.f);
+            if (gx * gx + gy * gy + gz * gz < kb.d[KNN_K - 1]) { t = u; break; }
+        }
+        if (t < 0) break;
         const int cx = ix + dx, cy = iy + dy, cz = iz + dz;
         const unsigned long long key = cell_key(cx, cy, cz);
         unsigned s = cell_slot(key, D.cap);
@@ -405,14 +420,14 @@ __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, f
         const int i0 = (int)b.x, i1 = (int)b.y, i2 = (int)b.z, i3 = (int)b.w;
         float4 p0, p1, p2, p3;
         p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);               // flag 0: not a live point
-        if (cnt > 0) p0 = __ldg(&m.pts[i0]);
-        if (cnt > 1) p1 = __ldg(&m.pts[i1]);
-        if (cnt > 2) p2 = __ldg(&m.pts[i2]);
-        if (cnt > 3) p3 = __ldg(&m.pts[i3]);
-        cell_consider(p0, i0, inv, cx, cy, cz, qx, qy, qz, kb);
-        cell_consider(p1, i1, inv, cx, cy, cz, qx, qy, qz, kb);
-        cell_consider(p2, i2, inv, cx, cy, cz, qx, qy, qz, kb);
-        cell_consider(p3, i3, inv, cx, cy, cz, qx, qy, qz, kb);
+        if (cnt > 0 && i0 >= 0) p0 = __ldg(&m.pts[i0]);
+        if (cnt > 1 && i1 >= 0) p1 = __ldg(&m.pts[i1]);
+        if (cnt > 2 && i2 >= 0) p2 = __ldg(&m.pts[i2]);
+        if (cnt > 3 && i3 >= 0) p3 = __ldg(&m.pts[i3]);
+        cell_consider(p0, i0, qx, qy, qz, kb);
+        cell_consider(p1, i1, qx, qy, qz, kb);
+        cell_consider(p2, i2, qx, qy, qz, kb);
+        cell_consider(p3, i3, qx, qy, qz, kb);
         if (cnt > CELL_INLINE) {
             const int* ext = D.ext + (size_t)((int)a.z - 1) * CELL_EXT;
 #pragma unroll 1
@@ -420,14 +435,14 @@ __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, f
                 const int4 e = __ldg(reinterpret_cast<const int4*>(ext + j));
                 const int n4 = cnt - CELL_INLINE - j;
                 p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n4 > 0) p0 = __ldg(&m.pts[e.x]);
-                if (n4 > 1) p1 = __ldg(&m.pts[e.y]);
-                if (n4 > 2) p2 = __ldg(&m.pts[e.z]);
-                if (n4 > 3) p3 = __ldg(&m.pts[e.w]);
-                cell_consider(p0, e.x, inv, cx, cy, cz, qx, qy, qz, kb);
-                cell_consider(p1, e.y, inv, cx, cy, cz, qx, qy, qz, kb);
-                cell_consider(p2, e.z, inv, cx, cy, cz, qx, qy, qz, kb);
-                cell_consider(p3, e.w, inv, cx, cy, cz, qx, qy, qz, kb);
+                if (n4 > 0 && e.x >= 0) p0 = __ldg(&m.pts[e.x]);
+                if (n4 > 1 && e.y >= 0) p1 = __ldg(&m.pts[e.y]);
+                if (n4 > 2 && e.z >= 0) p2 = __ldg(&m.pts[e.z]);
+                if (n4 > 3 && e.w >= 0) p3 = __ldg(&m.pts[e.w]);
+                cell_consider(p0, e.x, qx, qy, qz, kb);
+                cell_consider(p1, e.y, qx, qy, qz, kb);
+                cell_consider(p2, e.z, qx, qy, qz, kb);
+                cell_consider(p3, e.w, qx, qy, qz, kb);
             }
         }
     }

@@ -40,6 +40,8 @@ struct UpdArgs {
     double* red_g;         // [PSTRIDE] sums of this rank (mode 1 out, mode 3 in)
     PassLog* logs;
     P2PState* p2p;
+    unsigned long long* pub;   // publication block (32 words, own 256-byte line pair): the pose of the next pass as tagged words
+    unsigned nonce;        // unique per launch: stale words of an earlier launch can never look current
     int mode;              // 0: single GPU; 1: workers + reduction only (ncclAllReduce follows); 2: peer-memory exchange; 3: solver only, sums from red_g
     int max_passes;        // passes this launch may run (persistent: max_iter + 1; NCCL chain: 1)
     int search_only;       // 1: the kNN phase of one searching pass alone (neighbours + gate), for timing
@@ -66,6 +68,8 @@ template <bool EXTR> struct WorkerSm {
     static constexpr int STAGE = 32 * RowStage<EXTR>::RS + 96;
     double stage[UPD_WARPS][STAGE];
     double wred[UPD_WARPS][PSTRIDE];
+    unsigned pose_bits[28];
+    unsigned flags;
     int abort;
 };
 
@@ -76,6 +80,29 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 constexpr long long SPIN_LIMIT = 3000000000ll;       // ~1.5 s of SM clocks: a wedged peer must not hang the GPU
+
+// Publication of a pass's result to the worker blocks WITHOUT a fence: every 8-byte word carries 32 bits of payload and a
+// 32-bit tag (launch nonce, pass number) -- the data is the flag.  Words 0..27: the 14 doubles of the pose h_share_model
+// reads (pos, rot, offset_R_L_I, offset_T_L_I = x[0..13]) as halves; word 28: bit 0 converge, bit 1 done.
+constexpr int PUB_WORDS = 29;
+__device__ __forceinline__ unsigned pub_tag(unsigned nonce, int pass) { return (nonce << 8) | (unsigned)(pass & 0xff); }
+__device__ __forceinline__ void pub_store(unsigned long long* p, unsigned tag, unsigned payload) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)tag << 32) | payload) : "memory");
+}
+__device__ __forceinline__ unsigned long long pub_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// warp 0 of the solver block: x[0..13] and the flags, tagged for `pass`
+__device__ __forceinline__ void pub_publish(unsigned long long* pub, unsigned tag, const double* x, int converge, int done, int lane) {
+    if (lane < 28) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(x[lane >> 1]);
+        pub_store(pub + lane, tag, (lane & 1) ? (unsigned)(bits >> 32) : (unsigned)bits);
+    } else if (lane == 28) {
+        pub_store(pub + 28, tag, (converge ? 1u : 0u) | (done ? 2u : 0u));
+    }
+}
 
 // ============================================================================= workers
 // Everything of h_share_model for one scan point (laserMapping.cpp:650-692).  Warp-collective (the search hands the
@@ -306,7 +333,7 @@ __device__ __forceinline__ bool gj_cols(double (&c)[N], int* row_k, int lane) {
 // The H-dependent half of a pass, on the critical path (esekfom.hpp:1782-1834): gain, dx_, [+], convergence; publishes the new
 // pose; then, off the path, the log / covariance bookkeeping and -- on the pass that ends the update -- the final covariance.
 template <bool EXTR>
-__device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, int gen_next) {
+__device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, unsigned long long* pub, unsigned tag_next) {
     constexpr int NE = EXTR ? 12 : 6;
     constexpr int n = NDOF;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -385,10 +412,9 @@ __device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, int gen_nex
             }
             S.n_pass++;
             ctl->iter = S.iter; ctl->n_pass = S.n_pass; ctl->done = S.done; ctl->error = S.error;
-            __threadfence();
-            st_release(&ctl->gen, gen_next);
         }
         __syncthreads();
+        if (warp == 0) pub_publish(pub, tag_next, S.x, S.converge, S.done, lane);
         return;
     }
     // ------------------------------------------------------------------ x_.boxplus(dx_) (:1817); on the last pass also the congruence at dx_ (:1836-1876)
@@ -419,15 +445,16 @@ __device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, int gen_nex
     if (tid == 0) ctl->prof[6] = clock64();
     // ------------------------------------------------------------------ publish (warp 0 alone: no further block barrier on the path)
     if (warp == 0) {
+        pub_publish(pub, tag_next, S.xnew, S.converge, finish, lane);
+        if (lane == 0) ctl->prof[5] = clock64();
+    }
+    // ------------------------------------------------------------------ off the critical path
+    if (warp == 1) {
         if (lane < XLEN) ctl->x[lane] = S.xnew[lane];
         if (lane == 31) {
             ctl->t = S.t; ctl->converge = S.converge; ctl->iter = S.iter + 1; ctl->n_pass = S.n_pass + 1; ctl->done = finish;
         }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) { st_release(&ctl->gen, gen_next); ctl->prof[5] = clock64(); }
     }
-    // ------------------------------------------------------------------ off the critical path
     if (lg) {
         if (tid < 144) lg->HtH[tid] = S.HTH[tid];
         if (tid >= 160 && tid < 172) lg->Hth[tid - 160] = S.red[78 + tid - 160];
@@ -506,29 +533,43 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
         // ------------------------------------------------------------------ worker block
         WorkerSm<EXTR>& Wk = *reinterpret_cast<WorkerSm<EXTR>*>(smem_raw);
         const int wb = (int)blockIdx.x - 1;
-        const int gen0 = ld_acquire(&ctl->gen);
         if (tid == 0) Wk.abort = 0;
         for (int p = 0; p < a.max_passes; p++) {
-            if (p > 0) {
+            PoseS s;
+            bool searched;
+            if (p == 0) {
+                // the state this launch starts from is in the control block (uploaded / left by the previous launch)
+                if (__ldcg(&ctl->done)) return;
+                searched = __ldcg(&ctl->converge) != 0 || a.search_only;      // dyn_share.converge (laserMapping.cpp:667)
+                s = load_pose(ctl->x);
+            } else {
+                // later passes: wait for the solver block's publication of pass p (tagged words, see pub_publish)
+                const unsigned tag = pub_tag(a.nonce, p);
                 if (tid == 0) {
                     const long long t0 = clock64();
-                    while (ld_acquire(&ctl->gen) - gen0 < p) {
+                    while ((unsigned)(pub_load(a.pub + 28) >> 32) != tag) {
                         if (clock64() - t0 > SPIN_LIMIT) { Wk.abort = 1; atomicExch(&ctl->error, 3); break; }
-                        __nanosleep(40);
+                        __nanosleep(100);
                     }
                 }
                 __syncthreads();
                 if (Wk.abort) return;
-            }
-            if (__ldcg(&ctl->done)) return;
-            const bool searched = __ldcg(&ctl->converge) != 0 || a.search_only;      // dyn_share.converge (laserMapping.cpp:667)
-            PoseS s;
-            {
-                const double* x = ctl->x;
-                s.pos = d3(__ldcg(x + X_POS), __ldcg(x + X_POS + 1), __ldcg(x + X_POS + 2));
-                s.offT = d3(__ldcg(x + X_OFFT), __ldcg(x + X_OFFT + 1), __ldcg(x + X_OFFT + 2));
-                s.rot.x = __ldcg(x + X_ROT); s.rot.y = __ldcg(x + X_ROT + 1); s.rot.z = __ldcg(x + X_ROT + 2); s.rot.w = __ldcg(x + X_ROT + 3);
-                s.offR.x = __ldcg(x + X_OFFR); s.offR.y = __ldcg(x + X_OFFR + 1); s.offR.z = __ldcg(x + X_OFFR + 2); s.offR.w = __ldcg(x + X_OFFR + 3);
+                if (tid < PUB_WORDS) {
+                    unsigned long long w = pub_load(a.pub + tid);
+                    const long long t0 = clock64();
+                    while ((unsigned)(w >> 32) != tag && clock64() - t0 < SPIN_LIMIT) w = pub_load(a.pub + tid);
+                    if (tid < 28) Wk.pose_bits[tid] = (unsigned)w; else Wk.flags = (unsigned)w;
+                }
+                __syncthreads();
+                if (Wk.flags & 2u) return;
+                searched = (Wk.flags & 1u) != 0;
+                double x14[14];
+#pragma unroll
+                for (int i = 0; i < 14; i++) x14[i] = __longlong_as_double((long long)(((unsigned long long)Wk.pose_bits[2 * i + 1] << 32) | Wk.pose_bits[2 * i]));
+                s.pos = d3(x14[X_POS], x14[X_POS + 1], x14[X_POS + 2]);
+                s.rot.x = x14[X_ROT]; s.rot.y = x14[X_ROT + 1]; s.rot.z = x14[X_ROT + 2]; s.rot.w = x14[X_ROT + 3];
+                s.offR.x = x14[X_OFFR]; s.offR.y = x14[X_OFFR + 1]; s.offR.z = x14[X_OFFR + 2]; s.offR.w = x14[X_OFFR + 3];
+                s.offT = d3(x14[X_OFFT], x14[X_OFFT + 1], x14[X_OFFT + 2]);
             }
             double acc[3] = {0.0, 0.0, 0.0};
             double* stage = Wk.stage[warp];
@@ -549,9 +590,8 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
                 for (int w = 0; w < UPD_WARPS; w++) v += Wk.wred[w][tid];
                 __stcg(&a.partials[(size_t)wb * PSTRIDE + tid], v);
             }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) atomicAdd(&ctl->ticket, 1);
+            __syncthreads();                                // the block's partial is written ...
+            if (tid == 0) { __threadfence(); atomicAdd(&ctl->ticket, 1); }      // ... and ordered before the ticket by ONE fence
             if (a.mode == 1) return;
         }
         return;
@@ -559,25 +599,25 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
     // ------------------------------------------------------------------ solver block
     if (a.search_only) return;
     SolverSm& S = *reinterpret_cast<SolverSm*>(smem_raw);
-    const int gen0 = ld_acquire(&ctl->gen);
     sol_load(S, ctl);
-    for (int p = 0; p < a.max_passes && !S.done; p++) {
+    int p = 0;
+    for (; p < a.max_passes && !S.done; p++) {
         if (tid == 0) ctl->prof[0] = clock64();
         if (a.mode != 1) sol_prepare(S);                 // overlaps the workers' measurement
         if (tid == 0) ctl->prof[8] = clock64();
         if (a.mode != 3) {
             if (tid == 0) {
                 const long long t0 = clock64();
-                while (ld_acquire(&ctl->ticket) < nwork) {
+                while (ld_acquire(&ctl->ticket) < nwork * (p + 1)) {        // tickets only grow within a launch
                     if (clock64() - t0 > SPIN_LIMIT) { S.late = 2; break; }
                 }
-                ctl->ticket = 0;
             }
             __syncthreads();
             if (tid == 0) ctl->prof[9] = clock64();
             sol_reduce(S, a.partials, nwork);
             if (a.mode == 1) {
                 if (tid < NRED) a.red_g[tid] = S.red[tid];
+                if (tid == 0) ctl->ticket = 0;
                 return;
             }
         } else {
@@ -586,10 +626,10 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
         }
         if (a.mode == 2) sol_exchange(S, a.p2p);
         if (tid == 0) ctl->prof[1] = clock64();
-        sol_pass<EXTR>(S, ctl, a.logs, gen0 + p + 1);
+        sol_pass<EXTR>(S, ctl, a.logs, a.pub, pub_tag(a.nonce, p + 1));
         if (tid == 0) ctl->prof[7] = clock64();
     }
-    if (tid == 0) ctl->error = S.error | ctl->error;
+    if (tid == 0) { ctl->error = S.error | ctl->error; ctl->ticket = 0; }
     mirror_result(ctl);
 }
 

@@ -29,7 +29,6 @@ constexpr int PSTRIDE = 96;          // doubles per partial row (NRED = 92 padde
 // peer mailbox: [2 parities][P2P_MAX_RANKS slots][PSTRIDE values] x two tagged 8-byte words per value
 constexpr size_t P2P_MAIL_BYTES = sizeof(unsigned long long) * 2 * 2 * P2P_MAX_RANKS * PSTRIDE;
 constexpr int SEARCH_THREADS = 256;
-constexpr int SEARCH_C_THREADS = 128;
 constexpr int RESID_THREADS = 256;
 constexpr int MAX_LOGS = 16;
 
@@ -317,6 +316,20 @@ __device__ __forceinline__ void warp_accumulate(bool contrib, const double* h, d
     __syncwarp();
 }
 
+// the search of one scan point by one warp, results stored as h_share_model leaves them (laserMapping.cpp:670-671)
+__device__ __forceinline__ void search_point(const MapView& m, const ScanView& sc, int q, float qx, float qy, float qz, bool use_cells, int lane) {
+    KBest kb;
+    if (use_cells) knn_exact(m, qx, qy, qz, kb, lane);
+    else knn_query(m, qx, qy, qz, kb, lane);
+    float4 p;
+    const int cnt = knn_fetch_warp(m, kb, p, lane);
+    if (lane < KNN_K) sc.nearest[(size_t)q * KNN_K + lane] = p;
+    if (lane == KNN_K - 1) {
+        sc.nearest_cnt[q] = cnt;
+        sc.selected[q] = (cnt < KNN_K) ? 0 : (kb.d > 5.0f ? 0 : 1);          // laserMapping.cpp:671
+    }
+}
+
 // k_search -- the kNN half of h_share_model (laserMapping.cpp:667-672).  One warp per scan
 // point, a contiguous run of points per warp: the lanes first transform the warp's points to the
 // world frame thread-parallel (FP64, laserMapping.cpp:656-661), then the warp walks the map once
@@ -346,19 +359,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) k_search(MapView m, Scan
         const int cnt_chunk = min(32, wq1 - base);
         for (int l = 0; l < cnt_chunk; l++) {
             const float qx = __shfl_sync(FULL, wx, l), qy = __shfl_sync(FULL, wy, l), qz = __shfl_sync(FULL, wz, l);
-            const int q = base + l;
-            KBest kb;
-            knn_query(m, qx, qy, qz, kb, lane);
-            const int cnt = __popc(__ballot_sync(FULL, lane < KNN_K && kb.idx >= 0));
-            if (lane < KNN_K) {
-                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kb.idx >= 0) { p = m.pts[kb.idx]; p.w = m.payload[kb.idx]; }
-                sc.nearest[(size_t)q * KNN_K + lane] = p;
-            }
-            if (lane == KNN_K - 1) {
-                sc.nearest_cnt[q] = cnt;
-                sc.selected[q] = (cnt < KNN_K) ? 0 : (kb.d > 5.0f ? 0 : 1);          // laserMapping.cpp:671
-            }
+            search_point(m, sc, base + l, qx, qy, qz, false, lane);
         }
     }
 }
@@ -780,30 +781,29 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
     STAMP(7);
 }
 
-// k_search_c -- the same search through the map's hashed cell directory: one LANE per scan point looks at the 27 cells
-// around its point and proves its five neighbours exact; the few points it cannot prove (sparse surroundings, crowded
-// cells) are walked through the BVH by the whole warp (knn_lanes, map.cuh).  Same neighbours, same distances, bit for bit.
-__global__ void __launch_bounds__(SEARCH_C_THREADS) k_search_c(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
+// k_search_c -- k_search with the map's hashed cell directory in front of the BVH walk (knn_exact, map.cuh): one warp per
+// scan point, one lane per neighbour cell.  Same neighbours, same distances, bit for bit.
+__global__ void __launch_bounds__(SEARCH_THREADS, 4) k_search_c(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
     pdl_wait();
     pdl_launch();
     if (ctl->done || !ctl->converge) return;
     const int lane = threadIdx.x & 31;
-    const int q = sc.q_begin + blockIdx.x * SEARCH_C_THREADS + threadIdx.x;
-    const bool active = q < sc.q_end;
-    float wx = 0.f, wy = 0.f, wz = 0.f;
-    if (active) {
-        const PoseS s = load_pose(ctl->x);
-        body_to_world(s, __ldg(&sc.body[q]), wx, wy, wz);
+    const int gwarp = (blockIdx.x * SEARCH_THREADS + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * SEARCH_THREADS) >> 5;
+    const long long nq = sc.q_end - sc.q_begin;
+    const int wq0 = sc.q_begin + (int)(nq * gwarp / nwarps);
+    const int wq1 = sc.q_begin + (int)(nq * (gwarp + 1) / nwarps);
+    for (int base = wq0; base < wq1; base += 32) {
+        const int myq = base + lane;
+        float wx = 0.f, wy = 0.f, wz = 0.f;
+        if (myq < wq1) {
+            const PoseS s = load_pose(ctl->x);
+            body_to_world(s, __ldg(&sc.body[myq]), wx, wy, wz);
+        }
+        const int cnt_chunk = min(32, wq1 - base);
+        for (int l = 0; l < cnt_chunk; l++)
+            search_point(m, sc, base + l, __shfl_sync(FULL, wx, l), __shfl_sync(FULL, wy, l), __shfl_sync(FULL, wz, l), true, lane);
     }
-    TBest kb;
-    knn_lanes(m, active, wx, wy, wz, kb, lane);
-    if (!active) return;
-    float4 p[KNN_K];
-    const int cnt = knn_fetch(m, kb, p);
-#pragma unroll
-    for (int j = 0; j < KNN_K; j++) sc.nearest[(size_t)q * KNN_K + j] = p[j];
-    sc.nearest_cnt[q] = cnt;
-    sc.selected[q] = (cnt < KNN_K) ? 0 : (kb.d[KNN_K - 1] > 5.0f ? 0 : 1);          // laserMapping.cpp:671
 }
 
 // k_residual -- everything of h_share_model after the search (laserMapping.cpp:674-752), one
@@ -1116,6 +1116,8 @@ int Filter::init() {
     else if (search_occ_ == 5) FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<5>, SEARCH_THREADS, 0));
     else FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<4>, SEARCH_THREADS, 0));
     search_grid_max_ = sms_ * std::max(1, occ);
+    FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_c, SEARCH_THREADS, 0));
+    search_c_grid_max_ = sms_ * std::max(1, occ);
     if (const char* e = getenv("FASTLIO_B200_LEGACY")) fused_ = !(e[0] == '1');      // A/B: the split kernels of round 1
     FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_update<false>, UPD_THREADS, 0));
     upd_capacity_[0] = sms_ * std::max(1, occ);
@@ -1270,8 +1272,10 @@ int Filter::launch_update(int max_passes, int mode, int search_only) {
     a.logs = logs_.as<PassLog>(); a.p2p = p2p_.as<P2PState>();
     a.mode = mode; a.max_passes = max_passes; a.search_only = search_only;
     a.pub = pub_.as<unsigned long long>(); a.nonce = ++launch_nonce_;
+    { const char* e = getenv("FASTLIO_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
     const int cap = upd_capacity_[extrinsic_est_ ? 1 : 0];
-    int workers = mode == 3 ? 0 : std::min(cap - 1, (nq + UPD_THREADS - 1) / UPD_THREADS);
+    // every co-resident block works (a searching pass wants many warps in flight); small scans: at least 4 points per warp
+    int workers = mode == 3 ? 0 : std::min(cap - 1, (nq + 4 * UPD_WARPS - 1) / (4 * UPD_WARPS));
     if (workers < 0) workers = 0;
     if (extrinsic_est_) FL_CUDA(launch_pdl(k_update<true>, workers + 1, UPD_THREADS, stream(), pdl_, a));
     else FL_CUDA(launch_pdl(k_update<false>, workers + 1, UPD_THREADS, stream(), pdl_, a));
@@ -1283,8 +1287,8 @@ int Filter::launch_search_only() {
     const int nq = scan_.q_end - scan_.q_begin;
     if (fused()) return launch_update(1, 0, 1);
     if (search_mode_ == 1) {
-        const int tgrid = std::max(1, (nq + SEARCH_C_THREADS - 1) / SEARCH_C_THREADS);
-        FL_CUDA(launch_pdl(k_search_c, tgrid, SEARCH_C_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
+        const int cgrid = std::max(1, std::min(search_c_grid_max_, (nq * 32 + SEARCH_THREADS - 1) / SEARCH_THREADS));
+        FL_CUDA(launch_pdl(k_search_c, cgrid, SEARCH_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
         return FL_OK;
     }
     const int sgrid = std::max(1, std::min(search_grid_max_, (nq * 32 + SEARCH_THREADS - 1) / SEARCH_THREADS));

@@ -332,27 +332,23 @@ __device__ __forceinline__ void dir_move(const MapView& m, bool was_tomb, const 
     dir_add(m, p, slot, counters);
 }
 
-// Batched Nearest_Search: one lane per query (cell directory), BVH walk for what that cannot prove.
+// Batched Nearest_Search: one warp per query (cell directory, BVH walk for what that cannot prove).
 __global__ void __launch_bounds__(256) k_knn_batch(MapView m, const float4* __restrict__ q, int nq, int k,
                                                     float4* __restrict__ out_pts, float* __restrict__ out_d2,
                                                     int* __restrict__ out_cnt) {
     const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < nq; base += stride) {
-        const int i = base + lane;
-        const bool active = i < nq;
-        float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) qq = __ldg(&q[i]);
-        TBest kb;
-        knn_lanes(m, active, qq.x, qq.y, qq.z, kb, lane);
-        if (!active) continue;
-        float4 p[KNN_K];
-        const int cnt = knn_fetch(m, kb, p);
-#pragma unroll
-        for (int j = 0; j < KNN_K; j++) {
-            if (j < k) { out_pts[(size_t)i * k + j] = p[j]; out_d2[(size_t)i * k + j] = kb.d[j]; }
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += warps) {
+        const float4 qq = __ldg(&q[i]);
+        KBest kb;
+        knn_exact(m, qq.x, qq.y, qq.z, kb, lane);
+        float4 p;
+        const int cnt = min(k, knn_fetch_warp(m, kb, p, lane));
+        if (lane < k) {
+            out_pts[(size_t)i * k + lane] = p;
+            out_d2[(size_t)i * k + lane] = kb.d;
         }
-        out_cnt[i] = min(k, cnt);
+        if (lane == 0) out_cnt[i] = cnt;
     }
 }
 
@@ -822,7 +818,7 @@ int Map::knn(const float* q_xyzi, int nq, int k, float* out_pts, float* out_d2, 
     char* base = scratch_.as<char>();
     float4* d_q = (float4*)base; float4* d_p = (float4*)(base + qb); float* d_d = (float*)(base + qb + pb); int* d_c = (int*)(base + qb + pb + db);
     FL_CUDA(cudaMemcpyAsync(d_q, q_xyzi, qb, cudaMemcpyHostToDevice, stream_));
-    k_knn_batch<<<blocks_for(nq, 256), 256, 0, stream_>>>(v_, d_q, nq, k, d_p, d_d, d_c);
+    k_knn_batch<<<blocks_for((long long)nq * 32, 256), 256, 0, stream_>>>(v_, d_q, nq, k, d_p, d_d, d_c);
     FL_CUDA(cudaGetLastError());
     FL_CUDA(cudaMemcpyAsync(out_pts, d_p, pb, cudaMemcpyDeviceToHost, stream_));
     FL_CUDA(cudaMemcpyAsync(out_d2, d_d, db, cudaMemcpyDeviceToHost, stream_));

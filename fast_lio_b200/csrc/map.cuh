@@ -267,16 +267,19 @@ __device__ __forceinline__ void box_query(const MapView& m, const float* bmin, c
 }  // namespace fl
 
 // ============================================================================= cell directory: search
-// One THREAD per query over the hashed cell directory, exact by construction:
-//   * the 27 cells around the query are scanned nearest-first (own cell, faces, edges, corners); a cell is skipped when
-//     its nearest face is not closer than the current k-th best;
-//   * every point OUTSIDE the 3x3x3 block is at least g = (distance from the query to the block's faces) away, so the k
-//     best found are final when the k-th squared distance is strictly below g^2 (strict: the reference keeps the first of
-//     two equidistant candidates, ikd_Tree.cpp:1088) -- tests/cell_directory_model.py pins the rule on the CPU;
-//   * anything else (fewer than k points nearby, a crowded cell, coordinates beyond the key range) is NOT answered here:
-//     knn_lanes() hands those queries to the warp-cooperative BVH walk (knn_query), one at a time.
-// Squared distances use the same explicitly rounded float32 arithmetic as the BVH walk (sq_dist3), so either route
-// returns bit-identical distances.  All margins shrink the proven radius, never the searched set.
+// One WARP per query, one LANE per neighbour cell:
+//   1. lane t < 27 probes cell (own cell, faces, edges, corners -- nearest first) of the 3x3x3 block around the query:
+//      27 independent hashed look-ups in one step;
+//   2. the points the 27 cells list are numbered consecutively across the lanes (prefix sum of the counts) and scored 32 at a
+//      time, one candidate per lane -- a "virtual leaf" -- with the same k-best machinery as the BVH walk (knn_leaf);
+//      candidates of a cell whose nearest face is not closer than the current k-th best are not even loaded;
+//   3. every point OUTSIDE the block is at least g = (distance from the query to the block's faces) away, so the k best
+//      found are final when the k-th squared distance is strictly below g^2 (strict: the reference keeps the first of two
+//      equidistant candidates, ikd_Tree.cpp:1088) -- tests/cell_directory_model.py pins the rule on the CPU.
+// Anything else (fewer than k points nearby, a crowded cell, coordinates beyond the key range) is NOT answered here: the
+// caller walks the BVH for that query (knn_query), so the result is always the exact answer of KD_TREE::Nearest_Search.
+// Squared distances use the same explicitly rounded float32 arithmetic as the BVH walk (sq_dist3): either route returns
+// bit-identical distances.  All margins shrink the proven radius, never the searched set.
 namespace fl {
 
 __device__ __forceinline__ int cell_coord(float x, float inv_cell) {
@@ -292,211 +295,149 @@ __device__ __forceinline__ unsigned cell_slot(unsigned long long key, unsigned c
     return __umulhi((unsigned)(h >> 32) ^ (unsigned)h, cap);
 }
 
-struct TBest {                       // k best of one thread, ascending; empty entries: (+inf, -1)
-    float d[KNN_K];
-    int idx[KNN_K];
-    __device__ __forceinline__ void init() {
+// absorb one candidate per lane (key = bits of its squared distance, INF_BITS for none; idx = its slot) into the k-best list
+__device__ __forceinline__ void kbest_absorb(KBest& kb, unsigned key, int idx, int lane) {
+    if (kb.n == 0) {
+        // empty list: the r-th smallest goes straight to lane r -- no merge
+        unsigned best = INF_BITS;
 #pragma unroll
-        for (int i = 0; i < KNN_K; i++) { d[i] = INFINITY; idx[i] = -1; }
-    }
-    __device__ __forceinline__ void insert(float nd, int nidx) {       // nd < d[K-1]; equal distances keep their arrival order
-#pragma unroll
-        for (int i = KNN_K - 1; i > 0; i--) {
-            const bool shift = nd < d[i - 1];
-            const bool here = !shift && nd < d[i];
-            d[i] = shift ? d[i - 1] : (here ? nd : d[i]);
-            idx[i] = shift ? idx[i - 1] : (here ? nidx : idx[i]);
+        for (int r = 0; r < KNN_K; r++) {
+            best = __reduce_min_sync(FULL, key);
+            if (best == INF_BITS) break;
+            const int src = __ffs(__ballot_sync(FULL, key == best)) - 1;
+            const int bi = __shfl_sync(FULL, idx, src);
+            if (lane == r) { kb.d = __uint_as_float(best); kb.idx = bi; }
+            if (lane == src) key = INF_BITS;
+            kb.n = r + 1;
         }
-        if (nd < d[0]) { d[0] = nd; idx[0] = nidx; }
+        if (kb.n == KNN_K) kb.w = __uint_as_float(best);
+        return;
     }
-};
-
-// own cell, 6 faces, 12 edges, 8 corners
-static __constant__ signed char CELL_ORDER[27][4] = {
-    {0, 0, 0, 0},
-    {-1, 0, 0, 0}, {1, 0, 0, 0}, {0, -1, 0, 0}, {0, 1, 0, 0}, {0, 0, -1, 0}, {0, 0, 1, 0},
-    {-1, -1, 0, 0}, {-1, 1, 0, 0}, {1, -1, 0, 0}, {1, 1, 0, 0}, {-1, 0, -1, 0}, {-1, 0, 1, 0}, {1, 0, -1, 0}, {1, 0, 1, 0},
-    {0, -1, -1, 0}, {0, -1, 1, 0}, {0, 1, -1, 0}, {0, 1, 1, 0},
-    {-1, -1, -1, 0}, {-1, -1, 1, 0}, {-1, 1, -1, 0}, {-1, 1, 1, 0}, {1, -1, -1, 0}, {1, -1, 1, 0}, {1, 1, -1, 0}, {1, 1, 1, 0}};
-
-__host__ __device__ constexpr int cell_off(int t, int axis) {
-    // own cell, 6 faces, 12 edges, 8 corners -- the same order as CELL_ORDER
-    constexpr signed char T[27][3] = {
-        {0, 0, 0},
-        {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
-        {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1},
-        {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
-        {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
-    return T[t][axis];
-}
-
-// one candidate (a deleted point keeps its listing: it is skipped by its flag; struck-out listings arrive as all-zero points)
-__device__ __forceinline__ void cell_consider(const float4& p, int idx, float qx, float qy, float qz, TBest& kb) {
-    if (slot_valid(p)) {
-        const float dd = sq_dist3(qx, qy, qz, p.x, p.y, p.z);
-        if (dd < kb.d[KNN_K - 1]) kb.insert(dd, idx);
+#pragma unroll 1
+    for (int it = 0; it < KNN_K; it++) {
+        const unsigned best = __reduce_min_sync(FULL, key);
+        if (best >= __float_as_uint(kb.w)) break;       // nothing strictly closer than the k-th best is left (covers the marker)
+        const int src = __ffs(__ballot_sync(FULL, key == best)) - 1;
+        kb.insert(__uint_as_float(best), __shfl_sync(FULL, idx, src), lane);
+        if (lane == src) key = INF_BITS;
     }
 }
 
-// k-NN of one query by one thread.  Returns true when kb is PROVEN to be the exact answer.
-// A scan is only a few warps per SM, so a thread's own instruction and load chain IS the run time:
-//   phase 1  the keys of all 27 cells are probed with independent loads (hashes derived from the own cell's by constant
-//            offsets -- the hash is linear in the cell coordinates); this also brings the entries into L1;
-//   phase 2  only cells that exist and can still matter are visited, nearest first; a lane skips the cells it can prune
-//            BEFORE it joins the loop body, so that the lanes of a warp stay together; the (up to four inline) point loads
-//            of a cell are issued together.
-__device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, float qz, TBest& kb) {
+// Exact k-NN attempt for one query by one warp through the cell directory.  Returns true (warp-uniform) when kb is PROVEN
+// to be the exact answer; false: the caller must run knn_query().
+__device__ __forceinline__ bool cell_knn_warp(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
     const CellDir& D = m.dir;
     kb.init();
     if (D.cap == 0u) return false;
     const float inv = D.inv_cell;
     const int ix = cell_coord(qx, inv), iy = cell_coord(qy, inv), iz = cell_coord(qz, inv);
     if (abs(ix) >= CELL_CLAMP - 1 || abs(iy) >= CELL_CLAMP - 1 || abs(iz) >= CELL_CLAMP - 1) return false;
-    const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
-    const unsigned long long key0 = cell_key(ix, iy, iz);
-    constexpr unsigned long long G = 0x9E3779B97F4A7C15ull;
-    const unsigned long long h0 = key0 * G;
-    // ---- phase 1: bit t of `hit`: key found at its home slot; of `coll`: home slot taken by another cell
-    unsigned hit = 0u, coll = 0u;
-    {
-        unsigned long long got[27];
-#pragma unroll
-        for (int t = 0; t < 27; t++) {
-            // key(t) = key0 + dx 2^42 + dy 2^21 + dz  (no carries: every field stays inside its 21 bits), h = key * G mod 2^64
-            const long long dk = ((long long)cell_off(t, 0) << 42) + ((long long)cell_off(t, 1) << 21) + (long long)cell_off(t, 2);
-            const unsigned long long h = h0 + (unsigned long long)dk * G;
-            const unsigned slot = __umulhi((unsigned)(h >> 32) ^ (unsigned)h, D.cap);
-            got[t] = __ldg(reinterpret_cast<const unsigned long long*>(&tab[2 * (size_t)slot])) ^ (key0 + (unsigned long long)dk);
-        }
-#pragma unroll
-        for (int t = 0; t < 27; t++) {
-            const long long dk = ((long long)cell_off(t, 0) << 42) + ((long long)cell_off(t, 1) << 21) + (long long)cell_off(t, 2);
-            if (got[t] == 0ull) hit |= 1u << t;
-            else if (got[t] != key0 + (unsigned long long)dk) coll |= 1u << t;      // (stored ^ key) == key  <=>  free slot: no such cell
-        }
-    }
     const float c = D.cell;
     // distance from the query to the low / high face of its own cell, shrunk by more than any rounding of the cell arithmetic
     const float marg = 4e-6f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 2.f * c);
     const float lox = fmaxf(qx - (float)ix * c - marg, 0.f), hix = fmaxf((float)(ix + 1) * c - qx - marg, 0.f);
     const float loy = fmaxf(qy - (float)iy * c - marg, 0.f), hiy = fmaxf((float)(iy + 1) * c - qy - marg, 0.f);
     const float loz = fmaxf(qz - (float)iz * c - marg, 0.f), hiz = fmaxf((float)(iz + 1) * c - qz - marg, 0.f);
-    // ---- phase 2
-    bool crowded = false;
-    unsigned todo = hit | coll;
-#pragma unroll 1
-    while (true) {
-        // next cell of this lane whose nearest face is closer than the k-th best so far
-        int t = -1, dx = 0, dy = 0, dz = 0;
-        while (todo) {
-            const int u = __ffs(todo) - 1;
-            todo &= todo - 1;
-            dx = CELL_ORDER[u][0]; dy = CELL_ORDER[u][1]; dz = CELL_ORDER[u][2];
-            const float gx = dx < 0 ? lox : (dx > 0 ? hix : 0.f);
-            const float gy = dy < 0 ? loy : (dy > 0 ? hiy : 0.f);
-            const float gz = dz < 0 ? loz : (dz > 0 ? hiz : 0.f);
-            if (gx * gx + gy * gy + gz * gz < kb.d[KNN_K - 1]) { t = u; break; }
-        }
-        if (t < 0) break;
-        const int cx = ix + dx, cy = iy + dy, cz = iz + dz;
-        const unsigned long long key = cell_key(cx, cy, cz);
-        unsigned s = cell_slot(key, D.cap);
-        uint4 a = __ldg(&tab[2 * (size_t)s]);
-        if ((coll >> t) & 1u) {                                              // rare: walk the probe sequence
-            bool found = false;
-            for (unsigned probes = 0; probes < D.cap; probes++) {
-                const unsigned long long k = (unsigned long long)a.x | ((unsigned long long)a.y << 32);
-                if (k == key) { found = true; break; }
-                if (k == 0ull) break;
-                s = (s + 1 == D.cap) ? 0u : s + 1;
-                a = __ldg(&tab[2 * (size_t)s]);
-            }
-            if (!found) continue;
-        }
-        const int cnt = (int)a.w;
-        if (cnt > CELL_MAX || (cnt > CELL_INLINE && a.z == 0u)) { crowded = true; break; }
-        const uint4 b = __ldg(&tab[2 * (size_t)s + 1]);
-        // the inline points, loads first
-        const int i0 = (int)b.x, i1 = (int)b.y, i2 = (int)b.z, i3 = (int)b.w;
-        float4 p0, p1, p2, p3;
-        p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);               // flag 0: not a live point
-        if (cnt > 0 && i0 >= 0) p0 = __ldg(&m.pts[i0]);
-        if (cnt > 1 && i1 >= 0) p1 = __ldg(&m.pts[i1]);
-        if (cnt > 2 && i2 >= 0) p2 = __ldg(&m.pts[i2]);
-        if (cnt > 3 && i3 >= 0) p3 = __ldg(&m.pts[i3]);
-        cell_consider(p0, i0, qx, qy, qz, kb);
-        cell_consider(p1, i1, qx, qy, qz, kb);
-        cell_consider(p2, i2, qx, qy, qz, kb);
-        cell_consider(p3, i3, qx, qy, qz, kb);
-        if (cnt > CELL_INLINE) {
-            const int* ext = D.ext + (size_t)((int)a.z - 1) * CELL_EXT;
-#pragma unroll 1
-            for (int j = 0; j < cnt - CELL_INLINE; j += 4) {
-                const int4 e = __ldg(reinterpret_cast<const int4*>(ext + j));
-                const int n4 = cnt - CELL_INLINE - j;
-                p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n4 > 0 && e.x >= 0) p0 = __ldg(&m.pts[e.x]);
-                if (n4 > 1 && e.y >= 0) p1 = __ldg(&m.pts[e.y]);
-                if (n4 > 2 && e.z >= 0) p2 = __ldg(&m.pts[e.z]);
-                if (n4 > 3 && e.w >= 0) p3 = __ldg(&m.pts[e.w]);
-                cell_consider(p0, e.x, qx, qy, qz, kb);
-                cell_consider(p1, e.y, qx, qy, qz, kb);
-                cell_consider(p2, e.z, qx, qy, qz, kb);
-                cell_consider(p3, e.w, qx, qy, qz, kb);
-            }
-        }
-    }
-    if (crowded || kb.idx[KNN_K - 1] < 0) return false;
-    // proof: every point outside the 3x3x3 block is at least g away
-    const float g = fminf(fminf(fminf(lox, hix), fminf(loy, hiy)), fminf(loz, hiz)) + c - marg;
-    return kb.d[KNN_K - 1] < g * g;
-}
-
-// Exact k-NN for up to 32 queries of a warp (one per lane; `active` masks the tail).  The thread search answers what it
-// can prove; the rest goes through the cooperative BVH walk, one query at a time, and is handed back to its lane.
-__device__ __forceinline__ void knn_lanes(const MapView& m, bool active, float qx, float qy, float qz, TBest& kb, int lane) {
-    bool exact = true;
-    if (active) exact = cell_knn(m, qx, qy, qz, kb);
-    else kb.init();
-    unsigned todo = __ballot_sync(FULL, active && !exact);
-    if (todo && lane == 0 && m.dir.n_walked) atomicAdd(m.dir.n_walked, __popc(todo));
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const float fx = __shfl_sync(FULL, qx, src), fy = __shfl_sync(FULL, qy, src), fz = __shfl_sync(FULL, qz, src);
-        KBest w;
-        knn_query(m, fx, fy, fz, w, lane);
-#pragma unroll
-        for (int j = 0; j < KNN_K; j++) {
-            const float dj = __shfl_sync(FULL, w.d, j);
-            const int ij = __shfl_sync(FULL, w.idx, j);
-            if (lane == src) { kb.d[j] = dj; kb.idx[j] = ij; }
-        }
-    }
-}
-
-// The neighbours as the caller sees them: coordinates + intensity, nearest first; candidates whose squared distances
-// differ by less than 1e-10 are ordered by x like PointType_CMP does for the reference's heap (ikd_Tree.h:102-108).
-__device__ __forceinline__ int knn_fetch(const MapView& m, TBest& kb, float4 (&p)[KNN_K]) {
+    // ---- 1. this lane's cell: (dx, dy, dz) of entry `lane` of the nearest-first order, 6 bits each, ten per word
     int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < KNN_K; j++) {
-        p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kb.idx[j] >= 0) { p[j] = __ldg(&m.pts[kb.idx[j]]); p[j].w = __ldg(&m.payload[kb.idx[j]]); cnt++; }
+    unsigned ext = 0u;
+    uint4 b = make_uint4(0u, 0u, 0u, 0u);
+    float g2 = 0.f;                                   // squared distance from the query to this lane's cell
+    bool crowded = false;
+    if (lane < 27) {
+        const unsigned long long tbl = lane < 10 ? 0x498425159456515ull : (lane < 20 ? 0x292610661a411aull : 0x2a2a20a8220ull);
+        const unsigned code = (unsigned)(tbl >> (6 * (lane % 10))) & 63u;
+        const int dx = (int)(code & 3u) - 1, dy = (int)((code >> 2) & 3u) - 1, dz = (int)(code >> 4) - 1;
+        const float gx = dx < 0 ? lox : (dx > 0 ? hix : 0.f);
+        const float gy = dy < 0 ? loy : (dy > 0 ? hiy : 0.f);
+        const float gz = dz < 0 ? loz : (dz > 0 ? hiz : 0.f);
+        g2 = gx * gx + gy * gy + gz * gz;
+        const unsigned long long key = cell_key(ix + dx, iy + dy, iz + dz);
+        const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
+        unsigned s = cell_slot(key, D.cap);
+        for (unsigned probes = 0; probes < D.cap; probes++) {
+            const uint4 a = __ldg(&tab[2 * (size_t)s]);
+            const unsigned long long k = (unsigned long long)a.x | ((unsigned long long)a.y << 32);
+            if (k == key) {
+                cnt = (int)a.w; ext = a.z;
+                if (cnt > CELL_MAX || (cnt > CELL_INLINE && ext == 0u)) crowded = true;
+                else b = __ldg(&tab[2 * (size_t)s + 1]);
+                break;
+            }
+            if (k == 0ull) break;
+            s = (s + 1 == D.cap) ? 0u : s + 1;
+        }
     }
-    bool tie = false;
+    if (__any_sync(FULL, crowded)) return false;
+    // ---- 2. number the listed points across the lanes and score them 32 at a time
+    int incl = cnt;
 #pragma unroll
-    for (int j = 0; j + 1 < KNN_K; j++) tie |= kb.idx[j + 1] >= 0 && fabsf(kb.d[j + 1] - kb.d[j]) < 1e-10f;
-    if (tie) {
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    const int excl = incl - cnt;
+    for (int base = 0; base < total; base += 32) {
+        const int cand = base + lane;
+        // the cell of candidate `cand`: the last lane whose exclusive prefix is <= cand
+        int src = 0;
 #pragma unroll
-        for (int pass = 0; pass < KNN_K - 1; pass++) {
+        for (int step = 16; step > 0; step >>= 1) {
+            const int probe = src + step;
+            const int e = __shfl_sync(FULL, excl, probe & 31);
+            if (probe < 32 && e <= cand) src = probe;
+        }
+        const int j = cand - __shfl_sync(FULL, excl, src);
+        const unsigned bx = __shfl_sync(FULL, b.x, src), by = __shfl_sync(FULL, b.y, src), bz = __shfl_sync(FULL, b.z, src), bw = __shfl_sync(FULL, b.w, src);
+        const unsigned se = __shfl_sync(FULL, ext, src);
+        const float sg2 = __shfl_sync(FULL, g2, src);
+        int idx = -1;
+        if (cand < total && sg2 < kb.w) {              // its cell can still matter
+            if (j < CELL_INLINE) idx = (int)(j == 0 ? bx : (j == 1 ? by : (j == 2 ? bz : bw)));
+            else idx = __ldg(&D.ext[(size_t)(se - 1u) * CELL_EXT + (j - CELL_INLINE)]);
+        }
+        unsigned key = INF_BITS;
+        if (idx >= 0) {                                 // struck-out listings are -1
+            const float4 p = __ldg(&m.pts[idx]);
+            if (slot_valid(p)) key = __float_as_uint(sq_dist3(qx, qy, qz, p.x, p.y, p.z));      // deleted points keep their listing
+        }
+        kbest_absorb(kb, key, idx, lane);
+    }
+    // ---- 3. proof
+    if (kb.n < KNN_K && __popc(__ballot_sync(FULL, lane < KNN_K && kb.idx >= 0)) < KNN_K) return false;
+    const float g = fminf(fminf(fminf(lox, hix), fminf(loy, hiy)), fminf(loz, hiz)) + c - marg;
+    return kb.w < g * g;
+}
+
+// exact k-NN of one query by one warp: the cell directory when it can prove its answer, else the BVH walk
+__device__ __forceinline__ void knn_exact(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
+    if (cell_knn_warp(m, qx, qy, qz, kb, lane)) return;
+    if (lane == 0 && m.dir.cap && m.dir.n_walked) atomicAdd(m.dir.n_walked, 1);
+    knn_query(m, qx, qy, qz, kb, lane);
+}
+
+// The neighbours as the caller sees them, warp-wide: lane j < K returns neighbour j (coordinates + intensity), nearest
+// first; candidates whose squared distances differ by less than 1e-10 are ordered by x like PointType_CMP does for the
+// reference's heap (ikd_Tree.h:102-108).  Returns the number of neighbours found.
+__device__ __forceinline__ int knn_fetch_warp(const MapView& m, KBest& kb, float4& p, int lane) {
+    const bool have = lane < KNN_K && kb.idx >= 0;
+    p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have) { p = __ldg(&m.pts[kb.idx]); p.w = __ldg(&m.payload[kb.idx]); }
+    const int cnt = __popc(__ballot_sync(FULL, have));
+    // ties: odd-even transposition over the (at most five) entries, only when some adjacent pair ties
+    const float dn = __shfl_down_sync(FULL, kb.d, 1);
+    const bool tie = lane + 1 < cnt && fabsf(dn - kb.d) < 1e-10f;
+    if (__any_sync(FULL, tie)) {
 #pragma unroll
-            for (int j = 0; j + 1 < KNN_K - pass; j++) {
-                if (kb.idx[j + 1] >= 0 && fabsf(kb.d[j + 1] - kb.d[j]) < 1e-10f && p[j + 1].x < p[j].x) {
-                    const float4 tp = p[j]; p[j] = p[j + 1]; p[j + 1] = tp;
-                    const float td = kb.d[j]; kb.d[j] = kb.d[j + 1]; kb.d[j + 1] = td;
-                    const int ti = kb.idx[j]; kb.idx[j] = kb.idx[j + 1]; kb.idx[j + 1] = ti;
-                }
+        for (int pass = 0; pass < KNN_K; pass++) {
+            const int partner = ((lane + pass) & 1) ? lane - 1 : lane + 1;           // pairs (0,1)(2,3) / (1,2)(3,4) alternately
+            const int pl = min(max(partner, 0), 31);
+            const float od = __shfl_sync(FULL, kb.d, pl);
+            const int oi = __shfl_sync(FULL, kb.idx, pl);
+            const float ox = __shfl_sync(FULL, p.x, pl), oy = __shfl_sync(FULL, p.y, pl), oz = __shfl_sync(FULL, p.z, pl), ow = __shfl_sync(FULL, p.w, pl);
+            const bool both = partner >= 0 && lane < cnt && partner < cnt;
+            if (both && fabsf(od - kb.d) < 1e-10f) {
+                const bool lower = lane < partner;                                    // the lower lane keeps the smaller x
+                const bool take = lower ? (ox < p.x) : (ox > p.x);
+                if (take) { kb.d = od; kb.idx = oi; p = make_float4(ox, oy, oz, ow); }
             }
         }
     }

@@ -45,6 +45,7 @@ struct UpdArgs {
     int mode;              // 0: single GPU; 1: workers + reduction only (ncclAllReduce follows); 2: peer-memory exchange; 3: solver only, sums from red_g
     int max_passes;        // passes this launch may run (persistent: max_iter + 1; NCCL chain: 1)
     int search_only;       // 1: the kNN phase of one searching pass alone (neighbours + gate), for timing
+    int dbg;               // tuning switches (FASTLIO_B200_DBG)
 };
 
 struct SolverSm {
@@ -87,11 +88,11 @@ constexpr long long SPIN_LIMIT = 3000000000ll;       // ~1.5 s of SM clocks: a w
 constexpr int PUB_WORDS = 29;
 __device__ __forceinline__ unsigned pub_tag(unsigned nonce, int pass) { return (nonce << 8) | (unsigned)(pass & 0xff); }
 __device__ __forceinline__ void pub_store(unsigned long long* p, unsigned tag, unsigned payload) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)tag << 32) | payload) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)tag << 32) | payload) : "memory");
 }
 __device__ __forceinline__ unsigned long long pub_load(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 // warp 0 of the solver block: x[0..13] and the flags, tagged for `pass`
@@ -105,46 +106,29 @@ __device__ __forceinline__ void pub_publish(unsigned long long* pub, unsigned ta
 }
 
 // ============================================================================= workers
-// Everything of h_share_model for one scan point (laserMapping.cpp:650-692).  Warp-collective (the search hands the
-// queries it cannot prove to the whole warp).  Returns true when the point contributes a row.
+// Everything of h_share_model after the search for one scan point (laserMapping.cpp:674-692), one thread per point; the
+// neighbours / the gate of a searching pass were stored by this very warp a moment ago (search_point).  Returns true when
+// the point contributes a row.
 template <bool EXTR>
-__device__ __forceinline__ bool measure_fused(const MapView& m, const ScanView& sc, int q, bool active, const PoseS& s, bool searched,
-                                              bool search_only, int lane, double* h, double& z, float& absres) {
-    float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-    float wx = 0.f, wy = 0.f, wz = 0.f;
-    if (active) {
-        pb = __ldg(&sc.body[q]);
-        body_to_world(s, pb, wx, wy, wz);                                   // :656-661
-    }
-    bool sel = false;
-    float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
-    if (searched) {                                                         // :667
-        TBest kb;
-        knn_lanes(m, active, wx, wy, wz, kb, lane);                         // :670
-        if (active) {
-            float4 p[KNN_K];
-            const int cnt = knn_fetch(m, kb, p);
+__device__ __forceinline__ bool measure_thread(const ScanView& sc, int q, const PoseS& s, const float4& pb, float wx, float wy, float wz,
+                                               bool searched, double* h, double& z, float& absres) {
+    if (!__ldcg(&sc.selected[q])) return false;                                                 // :674
+    float pabcd[4];
+    bool sel = true;
+    if (searched) {
+        float pn[KNN_K][3];
 #pragma unroll
-            for (int j = 0; j < KNN_K; j++) sc.nearest[(size_t)q * KNN_K + j] = p[j];
-            sc.nearest_cnt[q] = cnt;
-            sel = cnt >= KNN_K && !(kb.d[KNN_K - 1] > 5.0f);                // :671
-            if (search_only) { sc.selected[q] = sel ? 1 : 0; return false; }
-            if (sel) {
-                float pn[KNN_K][3];
-#pragma unroll
-                for (int j = 0; j < KNN_K; j++) { pn[j][0] = p[j].x; pn[j][1] = p[j].y; pn[j][2] = p[j].z; }
-                sel = esti_plane_dev(pabcd, pn, 0.1f);                      // :678
-                if (sel) sc.plane[q] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
-            }
-        }
-    } else if (active) {
+        for (int j = 0; j < KNN_K; j++) { const float4 p = __ldcg(&sc.nearest[(size_t)q * KNN_K + j]); pn[j][0] = p.x; pn[j][1] = p.y; pn[j][2] = p.z; }
+        sel = esti_plane_dev(pabcd, pn, 0.1f);                                                  // :678
+        if (sel) sc.plane[q] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
+    } else {
         // a pass that does not search fits the plane to the SAME five neighbours (Nearest_Points persists, T3) and only
         // points whose fit and score succeeded last time are still selected: the fit is reused, not recomputed
-        sel = sc.selected[q] != 0;                                          // :674
-        if (sel) { const float4 pl = sc.plane[q]; pabcd[0] = pl.x; pabcd[1] = pl.y; pabcd[2] = pl.z; pabcd[3] = pl.w; }
+        const float4 pl = __ldcg(&sc.plane[q]);
+        pabcd[0] = pl.x; pabcd[1] = pl.y; pabcd[2] = pl.z; pabcd[3] = pl.w;
     }
     bool contrib = false;
-    if (active && sel) {
+    if (sel) {
         const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];             // :680
         const D3 p_body = d3(pb.x, pb.y, pb.z);
         const float score = (float)(1 - 0.9 * fabs((double)pd2) / sqrt(norm3(p_body)));        // :681 (T8)
@@ -154,7 +138,7 @@ __device__ __forceinline__ bool measure_fused(const MapView& m, const ScanView& 
             jacobian_row<EXTR>(s, pb, make_float4(pabcd[0], pabcd[1], pabcd[2], pd2), h, z);    // :723-751
         }
     }
-    if (active) sc.selected[q] = contrib ? 1 : 0;                                               // :677, :685
+    if (!contrib) sc.selected[q] = 0;                                                           // :677 (stays 1 otherwise, :685)
     return contrib;
 }
 
@@ -445,6 +429,7 @@ __device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, unsigned lo
     if (tid == 0) ctl->prof[6] = clock64();
     // ------------------------------------------------------------------ publish (warp 0 alone: no further block barrier on the path)
     if (warp == 0) {
+        if (lane == 0) ctl->prof[10] = clock64();
         pub_publish(pub, tag_next, S.xnew, S.converge, finish, lane);
         if (lane == 0) ctl->prof[5] = clock64();
     }
@@ -549,7 +534,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
                     const long long t0 = clock64();
                     while ((unsigned)(pub_load(a.pub + 28) >> 32) != tag) {
                         if (clock64() - t0 > SPIN_LIMIT) { Wk.abort = 1; atomicExch(&ctl->error, 3); break; }
-                        __nanosleep(100);
+                        __nanosleep((a.dbg & 1) ? 2000 : 100);
                     }
                 }
                 __syncthreads();
@@ -573,12 +558,32 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
             }
             double acc[3] = {0.0, 0.0, 0.0};
             double* stage = Wk.stage[warp];
-            const int q0 = a.sc.q_begin, q1 = a.sc.q_end;
-            for (int base = q0 + wb * UPD_THREADS + warp * 32; base < q1; base += nwork * UPD_THREADS) {
+            // this warp's run of points: balanced over all worker warps, the same run every pass (a point's cached neighbours,
+            // plane and flag are only ever touched by its own warp)
+            const int nwarps = nwork * UPD_WARPS, gwarp = wb * UPD_WARPS + warp;
+            const long long nq = a.sc.q_end - a.sc.q_begin;
+            const int wq0 = a.sc.q_begin + (int)(nq * gwarp / nwarps), wq1 = a.sc.q_begin + (int)(nq * (gwarp + 1) / nwarps);
+            for (int base = wq0; base < wq1; base += 32) {
                 const int q = base + lane;
+                const bool active = q < wq1;
+                float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+                float wx = 0.f, wy = 0.f, wz = 0.f;
+                if (active) {
+                    pb = __ldg(&a.sc.body[q]);
+                    body_to_world(s, pb, wx, wy, wz);                                       // laserMapping.cpp:656-661
+                }
+                if (searched) {                                                             // :667
+                    // one warp per point, one lane per neighbour cell (cell_knn_warp, map.cuh); BVH walk for what that cannot prove
+                    const int cnt_chunk = min(32, wq1 - base);
+                    for (int l = 0; l < cnt_chunk; l++)
+                        search_point(a.m, a.sc, base + l, __shfl_sync(FULL, wx, l), __shfl_sync(FULL, wy, l), __shfl_sync(FULL, wz, l), true, lane);
+                    __syncwarp();       // lanes 0..4 stored the neighbours and the gate; the owning lane reads them back below
+                }
+                if (a.search_only) continue;
                 double h[12]; double z = 0.0; float ar = 0.f;
-                const bool contrib = measure_fused<EXTR>(a.m, a.sc, q, q < q1, s, searched, a.search_only != 0, lane, h, z, ar);
-                if (!a.search_only) warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane, stage);
+                bool contrib = false;
+                if (active) contrib = measure_thread<EXTR>(a.sc, q, s, pb, wx, wy, wz, searched, h, z, ar);
+                warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane, stage);
             }
             if (a.search_only) return;
 #pragma unroll

@@ -39,7 +39,7 @@ SYMBOLS = [
     "fl_last_error", "fl_device_count", "fl_version", "fl_host_register", "fl_host_unregister", "fl_filter_debug_prof",
     "fl_map_create", "fl_map_destroy", "fl_map_set_downsample", "fl_map_build", "fl_map_size", "fl_map_validnum",
     "fl_map_knn", "fl_map_add_points", "fl_map_delete_boxes", "fl_map_flatten", "fl_map_tree_range",
-    "fl_map_rebuild", "fl_map_stats", "fl_map_set_cell_directory", "fl_map_dir_stats",
+    "fl_map_rebuild", "fl_map_stats", "fl_map_add_boxes", "fl_map_acquire_removed", "fl_map_set_cell_directory", "fl_map_dir_stats",
     "fl_filter_create", "fl_filter_destroy", "fl_filter_set_params", "fl_filter_set_solver", "fl_filter_set_search", "fl_filter_set_fused", "fl_filter_update",
     "fl_filter_map_incremental", "fl_filter_get_nearest", "fl_filter_get_selected", "fl_filter_get_pass_logs", "fl_filter_upload_scan",
     "fl_filter_upload_state", "fl_filter_run", "fl_filter_download_state", "fl_filter_sync",
@@ -76,6 +76,8 @@ def load():
     L.fl_map_add_points.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int]
     L.fl_map_delete_boxes.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.fl_map_flatten.argtypes = [C.c_void_p, _f32p, C.c_int]
+    L.fl_map_add_boxes.argtypes = [C.c_void_p, _f32p, C.c_int]
+    L.fl_map_acquire_removed.argtypes = [C.c_void_p, _f32p, C.c_int]
     L.fl_map_tree_range.argtypes = [C.c_void_p, _f32p]
     L.fl_map_rebuild.argtypes = [C.c_void_p]
     L.fl_map_stats.argtypes = [C.c_void_p, _i32p]
@@ -187,6 +189,17 @@ class KdTree:
     def Delete_Point_Boxes(self, boxes6) -> int:
         boxes6 = np.ascontiguousarray(boxes6, dtype=np.float32).reshape(-1, 6)
         return _check(self._L.fl_map_delete_boxes(self.h, boxes6, len(boxes6)))
+
+    # KD_TREE::Add_Point_Boxes
+    def Add_Point_Boxes(self, boxes6) -> int:
+        boxes6 = np.ascontiguousarray(boxes6, dtype=np.float32).reshape(-1, 6)
+        return _check(self._L.fl_map_add_boxes(self.h, boxes6, len(boxes6)))
+
+    # KD_TREE::acquire_removed_points
+    def acquire_removed_points(self, cap: int = 1 << 20) -> np.ndarray:
+        out = np.zeros((max(cap, 1), 4), dtype=np.float32)
+        n = _check(self._L.fl_map_acquire_removed(self.h, out, cap))
+        return out[:min(n, cap)].copy()
 
     # KD_TREE::flatten(Root_Node, ..., NOT_RECORD)
     def flatten(self) -> np.ndarray:

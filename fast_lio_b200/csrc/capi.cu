@@ -112,6 +112,18 @@ int fl_map_delete_boxes(fl_map_t* m, const float* boxes6, int nb) {
     int rc = m->impl->delete_boxes(boxes6, nb, &deleted);
     return rc == FL_OK ? deleted : rc;
 }
+int fl_map_add_boxes(fl_map_t* m, const float* boxes6, int nb) {
+    MAP_GUARD(m);
+    int revived = 0;
+    int rc = m->impl->add_boxes(boxes6, nb, &revived);
+    return rc == FL_OK ? revived : rc;
+}
+int fl_map_acquire_removed(fl_map_t* m, float* out, int cap) {
+    MAP_GUARD(m);
+    int n = 0;
+    int rc = m->impl->acquire_removed(out, cap, &n);
+    return rc == FL_OK ? n : rc;
+}
 int fl_map_flatten(fl_map_t* m, float* out, int cap) {
     MAP_GUARD(m);
     int n = 0;

@@ -39,7 +39,7 @@ void DeviceBuffer::release() {
 
 // counters_ layout
 enum Counter { C_LEAF_USED = 0, C_DELETED, C_ADDED, C_GROUPS, C_NINSERT, C_TOMB, C_ERROR, C_COMPACT,
-               C_DIR_CELLS, C_DIR_EXT, C_DIR_CROWDED, C_DIR_ERROR, C_DIR_WALKED, C_COUNT = 16 };
+               C_DIR_CELLS, C_DIR_EXT, C_DIR_CROWDED, C_DIR_ERROR, C_DIR_WALKED, C_REMOVED, C_REVIVED, C_COUNT = 16 };
 
 // ============================================================================= kernels
 // ----------------------------------------------------------------------------- k-d partition build
@@ -355,21 +355,48 @@ __global__ void __launch_bounds__(256) k_knn_batch(MapView m, const float4* __re
 // Delete_Point_Boxes: every slot tests itself against the boxes (half-open, ikd_Tree.cpp:796).
 // A flat pass over the leaf array is bandwidth-trivial on HBM3e (16 B per slot) and needs
 // no tree descent, no lazy flags and no push-down.
-__global__ void k_delete_boxes(MapView m, const float* __restrict__ boxes, int nb, int n_leaf_used, int* counters) {
+__global__ void k_delete_boxes(MapView m, const float* __restrict__ boxes, int nb, int n_leaf_used, int* counters,
+                               float4* __restrict__ removed, int removed_cap) {
     const long long total = (long long)n_leaf_used * LEAF;
+    const int lane = threadIdx.x & 31;
     int local = 0;
-    for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < total;
-         slot += (long long)gridDim.x * blockDim.x) {
-        float4 p = m.pts[slot];
-        if (slot_valid(p)) {
-            bool hit = false;
-            for (int b = 0; b < nb && !hit; b++) hit = in_box(p, &boxes[b * 6], &boxes[b * 6 + 3]);
+    for (long long base = (blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const long long slot = base + lane;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool hit = false;
+        if (slot < total) {
+            p = m.pts[slot];
+            if (slot_valid(p)) for (int b = 0; b < nb && !hit; b++) hit = in_box(p, &boxes[b * 6], &boxes[b * 6 + 3]);
             if (hit) { m.pts[slot].w = __int_as_float(SLOT_TOMB); local++; }
+        }
+        if (removed) {                                     // history for acquire_removed_points (ikd_Tree.cpp:661-676)
+            const unsigned mask = __ballot_sync(FULL, hit);
+            int off = 0;
+            if (lane == 0 && mask) off = atomicAdd(&counters[C_REMOVED], __popc(mask));
+            off = __shfl_sync(FULL, off, 0);
+            const int at = off + __popc(mask & ((1u << lane) - 1));
+            if (hit && at < removed_cap) { p.w = m.payload[slot]; removed[at] = p; }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counters[C_DELETED], local);
+    if (lane == 0 && local) atomicAdd(&counters[C_DELETED], local);
+}
+// Add_Point_Boxes (ikd_Tree.cpp:576-603 -> Add_by_range :854-934): points deleted by Delete_Point_Boxes that lie in the boxes
+// and have not been overwritten since come back (points removed by down-sampling do not, as in the reference)
+__global__ void k_revive_boxes(MapView m, const float* __restrict__ boxes, int nb, int n_leaf_used, int* counters) {
+    const long long total = (long long)n_leaf_used * LEAF;
+    int local = 0;
+    for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
+        const float4 p = m.pts[slot];
+        if (__float_as_int(p.w) != SLOT_TOMB) continue;
+        bool hit = false;
+        for (int b = 0; b < nb && !hit; b++) hit = in_box(p, &boxes[b * 6], &boxes[b * 6 + 3]);
+        if (hit) { m.pts[slot].w = __int_as_float(SLOT_VALID); local++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counters[C_REVIVED], local);
 }
 
 // Compaction of every valid point (x, y, z, intensity) -- flatten() and the input of rebuild().
@@ -459,7 +486,7 @@ struct BoxKill {       // pass 2: invalidate every valid point inside the voxel 
         while (l >= 0) {
             const int slot = l * LEAF + lane;
             const float4 p = m.pts[slot];
-            if (slot_valid(p) && in_box(p, vb.bmin, vb.bmax) && slot != keep) m.pts[slot].w = __int_as_float(SLOT_TOMB);
+            if (slot_valid(p) && in_box(p, vb.bmin, vb.bmax) && slot != keep) m.pts[slot].w = __int_as_float(SLOT_TOMB_DS);
             l = m.next[l];
         }
     }
@@ -557,7 +584,7 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
         while (!placed) {
             const float4 cur = m.pts[leaf * LEAF + lane];
             const int w = __float_as_int(cur.w);
-            unsigned freem = __ballot_sync(FULL, w == SLOT_FREE || w == SLOT_TOMB);
+            unsigned freem = __ballot_sync(FULL, w == SLOT_FREE || w == SLOT_TOMB || w == SLOT_TOMB_DS);
             while (freem && !placed) {
                 const int s = __ffs(freem) - 1;
                 // what lane s saw in the slot: a tombstone still carries the deleted point (and its directory listing)
@@ -570,7 +597,7 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
                     if (lane == 0) {
                         m.payload[leaf * LEAF + s] = p.w;
                         m.pts[leaf * LEAF + s] = make_float4(p.x, p.y, p.z, __int_as_float(SLOT_VALID));
-                        dir_move(m, seen == SLOT_TOMB, make_float4(ox, oy, oz, 0.f), p, leaf * LEAF + s, counters);
+                        dir_move(m, seen != SLOT_FREE, make_float4(ox, oy, oz, 0.f), p, leaf * LEAF + s, counters);
                     }
                     placed = true;
                 } else {
@@ -616,7 +643,7 @@ Map::Map(int device, float downsample_size) : device_(device), downsample_(downs
 
 Map::~Map() {
     cudaSetDevice(device_);
-    pts_.release(); payload_.release(); next_.release(); counters_.release(); dir_tab_.release(); dir_ext_.release();
+    pts_.release(); payload_.release(); next_.release(); counters_.release(); dir_tab_.release(); dir_ext_.release(); removed_.release();
     for (int k = 0; k < MAX_LEVELS; k++) ebox_[k].release();
     segid_.release(); segtab_[0].release(); segtab_[1].release(); bbox_.release();
     src_.release(); keys_in_.release(); keys_out_.release(); vals_in_.release(); vals_out_.release();
@@ -838,17 +865,73 @@ int Map::delete_boxes(const float* boxes6, int nb, int* deleted) {
     FL_CUDA(cudaMemcpyAsync(scratch_.ptr, boxes6, sizeof(float) * 6 * (size_t)nb, cudaMemcpyHostToDevice, stream_));
     FL_CUDA(cudaMemsetAsync(&counters_.as<int>()[C_DELETED], 0, sizeof(int), stream_));
     const int used = h_counters_[C_LEAF_USED];
-    k_delete_boxes<<<blocks_for((long long)used * LEAF, 256), 256, 0, stream_>>>(v_, scratch_.as<float>(), nb, used, counters_.as<int>());
+    if (record_removed_) {      // room for the worst case on top of what is already recorded
+        const size_t want = (size_t)n_removed_ + (size_t)n_valid_;
+        if (want * sizeof(float4) > removed_.bytes) {
+            DeviceBuffer bigger;
+            FL_CHECK(bigger.reserve(sizeof(float4) * (want + want / 2)));
+            if (n_removed_) FL_CUDA(cudaMemcpyAsync(bigger.ptr, removed_.ptr, sizeof(float4) * (size_t)n_removed_, cudaMemcpyDeviceToDevice, stream_));
+            FL_CUDA(cudaStreamSynchronize(stream_));
+            removed_.release();
+            removed_ = bigger;
+        }
+    }
+    k_delete_boxes<<<blocks_for((long long)used * LEAF, 256), 256, 0, stream_>>>(v_, scratch_.as<float>(), nb, used, counters_.as<int>(),
+                                                                                   record_removed_ ? removed_.as<float4>() : nullptr,
+                                                                                   (int)std::min<size_t>(removed_.bytes / sizeof(float4), 0x7fffffff));
     FL_CUDA(cudaGetLastError());
     FL_CUDA(cudaMemcpyAsync(&h_counters_[C_DELETED], &counters_.as<int>()[C_DELETED], sizeof(int), cudaMemcpyDeviceToHost, stream_));
     FL_CUDA(cudaStreamSynchronize(stream_));
     const int d = h_counters_[C_DELETED];
+    if (record_removed_) n_removed_ += d;
     if (d > 0) {
         n_valid_ -= d; n_tomb_ += d;
         FL_CHECK(refit());          // tighten every AABB ("box-delete by refit")
         FL_CHECK(maybe_rebuild());
     }
     if (deleted) *deleted = d;
+    return FL_OK;
+}
+
+// KD_TREE::acquire_removed_points (ikd_Tree.cpp:661-676): the points Delete_Point_Boxes removed since the last call.  Recording
+// starts with the first call (the reference's caller asks before every box delete, laserMapping.cpp:273-275).
+int Map::acquire_removed(float* out_xyzi, int cap, int* n_out) {
+    FL_CUDA(cudaSetDevice(device_));
+    const int n = n_removed_;
+    if (n_out) *n_out = n;
+    if (!record_removed_) {
+        record_removed_ = true;
+        FL_CUDA(cudaMemsetAsync(&counters_.as<int>()[C_REMOVED], 0, sizeof(int), stream_));
+        return FL_OK;
+    }
+    if (n > 0 && out_xyzi && cap > 0)
+        FL_CUDA(cudaMemcpyAsync(out_xyzi, removed_.ptr, sizeof(float4) * (size_t)std::min(n, cap), cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaMemsetAsync(&counters_.as<int>()[C_REMOVED], 0, sizeof(int), stream_));
+    FL_CUDA(cudaStreamSynchronize(stream_));
+    n_removed_ = 0;
+    return FL_OK;
+}
+
+// KD_TREE::Add_Point_Boxes (ikd_Tree.cpp:576-603)
+int Map::add_boxes(const float* boxes6, int nb, int* revived) {
+    if (revived) *revived = 0;
+    if (nb < 0 || (nb > 0 && !boxes6)) { set_last_error("add_boxes: bad arguments"); return FL_ERR_ARG; }
+    if (nb == 0) return FL_OK;
+    FL_CUDA(cudaSetDevice(device_));
+    FL_CHECK(scratch_.reserve(sizeof(float) * 6 * (size_t)nb));
+    FL_CUDA(cudaMemcpyAsync(scratch_.ptr, boxes6, sizeof(float) * 6 * (size_t)nb, cudaMemcpyHostToDevice, stream_));
+    FL_CUDA(cudaMemsetAsync(&counters_.as<int>()[C_REVIVED], 0, sizeof(int), stream_));
+    const int used = h_counters_[C_LEAF_USED];
+    k_revive_boxes<<<blocks_for((long long)used * LEAF, 256), 256, 0, stream_>>>(v_, scratch_.as<float>(), nb, used, counters_.as<int>());
+    FL_CUDA(cudaGetLastError());
+    FL_CUDA(cudaMemcpyAsync(&h_counters_[C_REVIVED], &counters_.as<int>()[C_REVIVED], sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    FL_CUDA(cudaStreamSynchronize(stream_));
+    const int r = h_counters_[C_REVIVED];
+    if (r > 0) {
+        n_valid_ += r; n_tomb_ = std::max(0, n_tomb_ - r);
+        FL_CHECK(refit());          // the boxes were tightened when the points went away
+    }
+    if (revived) *revived = r;
     return FL_OK;
 }
 

@@ -65,8 +65,9 @@ struct MapView {
     int leaf_cap;                    // allocated leaves (main + overflow pool)
 };
 
-// slot flag (bits of pts[].w): never used / being written by an insert / live point / deleted point (still listed in the cell directory)
-constexpr int SLOT_FREE = 0, SLOT_VALID = 1, SLOT_BUSY = 2, SLOT_TOMB = 3;
+// slot flag (bits of pts[].w): never used / live point / being written by an insert / deleted by Delete_Point_Boxes (Add_Point_Boxes
+// may revive it) / deleted by the down-sampling of Add_Points.  Deleted points keep their listing in the cell directory.
+constexpr int SLOT_FREE = 0, SLOT_VALID = 1, SLOT_BUSY = 2, SLOT_TOMB = 3, SLOT_TOMB_DS = 4;
 __device__ __forceinline__ bool slot_valid(const float4& p) { return __float_as_int(p.w) == SLOT_VALID; }
 
 // ----------------------------------------------------------------------------- k-best list

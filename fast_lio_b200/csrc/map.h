@@ -32,6 +32,9 @@ public:
     // KD_TREE::Add_Points (ikd_Tree.cpp:478-573); *added = the reference's return value
     int add_points(const float* pts_xyzi, int n, bool downsample_on, int* added);
     int add_points_device(const float4* d_pts_xyzi, int n, bool downsample_on, int* added);
+    // KD_TREE::Add_Point_Boxes (ikd_Tree.cpp:576-603) / acquire_removed_points (:661-676)
+    int add_boxes(const float* boxes6, int nb, int* revived);
+    int acquire_removed(float* out_xyzi, int cap, int* n_out);
     // all valid points, unordered (flatten(Root_Node, ..., NOT_RECORD), ikd_Tree.cpp:1627-1658)
     int flatten(float* out_xyzi, int cap, int* n_out);
     // re-sort every valid point into fresh, evenly filled leaves (ikd-Tree's Rebuild, ikd_Tree.cpp:736-764)
@@ -73,7 +76,9 @@ private:
     int n_valid_ = 0, n_tomb_ = 0, n_rebuilds_ = 0;
     bool built_ = false;
 
-    DeviceBuffer pts_, payload_, next_, counters_, dir_tab_, dir_ext_;
+    DeviceBuffer pts_, payload_, next_, counters_, dir_tab_, dir_ext_, removed_;
+    bool record_removed_ = false;
+    int n_removed_ = 0;
     bool dir_enabled_ = true;
     float cell_override_ = 0.f;           // 0: cell edge = 2 x downsample size
     size_t dir_min_cap_ = 0, dir_min_ext_ = 0;

@@ -236,7 +236,19 @@ __device__ void sol_reduce(SolverSm& S, const double* __restrict__ partials, int
 #pragma unroll
         for (int w = 0; w < UPD_WARPS; w++) v += S.wred[w][tid];
         S.red[tid] = v;
+        if (tid < 78) {                       // H^T H in full 12 x 12 form for the gain (tid -> (a <= b) of the packed upper triangle)
+            int a = 0, rem = tid;
+            while (rem >= 12 - a) { rem -= 12 - a; a++; }
+            const int b = a + rem;
+            S.HTH[a * 12 + b] = v; S.HTH[b * 12 + a] = v;
+        }
     }
+    __syncthreads();
+}
+// the same expansion for sums that did not come through sol_reduce (peer exchange, NCCL)
+__device__ void sol_expand(SolverSm& S) {
+    const int tid = threadIdx.x;
+    if (tid < 144) { const int a = tid / 12, b = tid - a * 12; S.HTH[tid] = S.red[a <= b ? tri12(a, b) : tri12(b, a)]; }
     __syncthreads();
 }
 
@@ -314,43 +326,40 @@ __device__ __forceinline__ bool gj_cols(double (&c)[N], int* row_k, int lane) {
     return ok;
 }
 
-// The H-dependent half of a pass, on the critical path (esekfom.hpp:1782-1834): gain, dx_, [+], convergence; publishes the new
-// pose; then, off the path, the log / covariance bookkeeping and -- on the pass that ends the update -- the final covariance.
+// The H-dependent half of a pass (esekfom.hpp:1782-1834).  The critical path -- gain, dx_, convergence, [+] on the pose the
+// measurement model reads, publication -- runs in WARP 0 ALONE, with the system in registers and no block barrier; everything
+// else ([+] on velocity / biases / gravity, the log, the covariance bookkeeping and, on the pass that ends the update, the final
+// covariance) follows the publication.
 template <bool EXTR>
 __device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, unsigned long long* pub, unsigned tag_next) {
     constexpr int NE = EXTR ? 12 : 6;
     constexpr int n = NDOF;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double Rinv = 1.0 / S.R;
-    // ------------------------------------------------------------------ warp 0: gain and dx_ with the system in registers
     if (warp == 0) {
         const int effct = (int)(S.red[90] + 0.5);
-        if (effct >= 1) {
-            for (int e = lane; e < 144; e += 32) { const int a = e / 12, b = e - a * 12; S.HTH[e] = S.red[a <= b ? tri12(a, b) : tri12(b, a)]; }
-            __syncwarp();
-            // lane j < NE: column j of A = I + H^T H P_11 / R;  lane NE: H^T h + H^T H dx_new;  lanes NE+1 .. 2NE: H^T H
-            double c[NE];
-            if (lane < NE) {
+        bool ok = true;
+        int finish = 0;
+        if (effct >= 1 && !S.late) {
+            // lane j <= 2 NE holds column j of [A | rhs | H^T H] as  base + H^T H u:
+            //   j < NE   : A = I + H^T H P_11 / R          u = P_11[:, j] / R       base = e_j
+            //   j == NE  : H^T h + H^T H dx_new[:ne]       u = dx_new[:ne]          base = H^T h
+            //   j > NE   : H^T H                           u = e_(j - NE - 1)       base = 0
+            double c[NE], u[NE];
 #pragma unroll
-                for (int r = 0; r < NE; r++) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NE; k++) v = fma(S.HTH[r * 12 + k], S.Pt[k * n + lane] * Rinv, v);
-                    c[r] = v + (r == lane ? 1.0 : 0.0);
-                }
-            } else if (lane == NE) {
-#pragma unroll
-                for (int r = 0; r < NE; r++) {
-                    double v = S.red[78 + r];
-#pragma unroll
-                    for (int k = 0; k < NE; k++) v = fma(S.HTH[r * 12 + k], S.dxn[k], v);
-                    c[r] = v;
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < NE; r++) c[r] = lane <= 2 * NE ? S.HTH[r * 12 + (lane - NE - 1)] : 0.0;
+            for (int k = 0; k < NE; k++) {
+                const double pk = S.Pt[k * n + (lane < NE ? lane : 0)] * Rinv;
+                u[k] = lane < NE ? pk : (lane == NE ? S.dxn[k] : (k == lane - NE - 1 ? 1.0 : 0.0));
             }
-            const bool ok = gj_cols<NE>(c, S.row_k, lane);
+#pragma unroll
+            for (int r = 0; r < NE; r++) {
+                double v = lane < NE ? (r == lane ? 1.0 : 0.0) : (lane == NE ? S.red[78 + r] : 0.0);
+#pragma unroll
+                for (int k = 0; k < NE; k++) v = fma(S.HTH[r * 12 + k], u[k], v);
+                c[r] = lane <= 2 * NE ? v : 0.0;
+            }
+            ok = gj_cols<NE>(c, S.row_k, lane);
+            if (lane == 0) ctl->prof[4] = clock64();
             if (lane >= NE && lane <= 2 * NE) {
 #pragma unroll
                 for (int r = 0; r < NE; r++) S.Wm[S.row_k[r] * 13 + (lane - NE)] = c[r];
@@ -365,87 +374,81 @@ __device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, unsigned lo
                 S.dxu[lane] = d;
             }
             const unsigned over = __ballot_sync(FULL, lane < n && fabs(d) > S.limit[lane]);              // :1818-1825
-            if (lane == 0) {
-                int converge = over ? 0 : 1;
-                int t = S.t;
-                if (converge) t++;
-                if (!t && S.iter == S.max_iter - 2) converge = 1;               // T2: force a re-search on the last pass (:1829-1832)
-                S.finish = (t > 1 || S.iter == S.max_iter - 1) ? 1 : 0;        // :1834
-                S.searched = S.converge;
-                S.t = t; S.converge = converge; S.ok = ok ? 1 : 0;
+            int converge = over ? 0 : 1;
+            int t = S.t;
+            if (converge) t++;
+            if (!t && S.iter == S.max_iter - 2) converge = 1;               // T2: force a re-search on the last pass (:1829-1832)
+            finish = (t > 1 || S.iter == S.max_iter - 1) ? 1 : 0;           // :1834
+            __syncwarp();
+            if (lane == 0) ctl->prof[6] = clock64();
+            if (ok) {
+                // x_.boxplus(dx_) on the pose (:1817): lanes 0 / 1 the two rotations (one instruction stream), lanes 2..7 pos, offset_T
+                if (lane < 2) {
+                    const int idx = lane == 0 ? 3 : 6, xo = lane == 0 ? X_ROT : X_OFFR;
+                    stq(S.xnew + xo, qmul(ldq(S.x + xo), so3_exp(d3(S.dxu[idx], S.dxu[idx + 1], S.dxu[idx + 2]))));   // SOn.hpp:233-236
+                } else if (lane < 8) {
+                    const int b = (lane - 2) / 3, cc = (lane - 2) % 3;
+                    const int dof = b == 0 ? 0 : 9, xo = b == 0 ? X_POS : X_OFFT;
+                    S.xnew[xo + cc] = S.x[xo + cc] + S.dxu[dof + cc];                                                  // vect.hpp:117-119
+                }
+                __syncwarp();
+                if (lane == 0) ctl->prof[10] = clock64();
+                pub_publish(pub, tag_next, S.xnew, converge, finish, lane);
+                if (lane == 0) { ctl->prof[5] = clock64(); S.searched = S.converge; S.t = t; S.converge = converge; }
             }
         }
-        if (lane == 0) S.effct = effct;
+        if (lane == 0) { S.effct = effct; S.ok = ok ? 1 : 0; S.finish = finish; }
+        if (effct < 1 || !ok || S.late) {
+            // ---- invalid pass (laserMapping.cpp:708-713, esekfom.hpp:1638-1641: `continue`) or a device-side failure
+            if (lane == 0) {
+                if (effct < 1 && !S.late) { S.iter++; if (S.iter >= S.max_iter) S.done = 1; S.searched = S.converge; }
+                else { S.error = S.late ? (S.late == 2 ? 3 : 2) : 1; S.done = 1; }     // 2: a peer never delivered; 3: the workers never reported; 1: singular system
+            }
+            __syncwarp();
+            pub_publish(pub, tag_next, S.x, S.converge, S.done, lane);
+        }
     }
     __syncthreads();
-    if (tid == 0) ctl->prof[4] = clock64();
     PassLog* lg = (logs && S.n_pass < MAX_LOGS) ? &logs[S.n_pass] : nullptr;
-    // ------------------------------------------------------------------ invalid pass (laserMapping.cpp:708-713, esekfom.hpp:1638-1641)
     if (S.effct < 1 || !S.ok || S.late) {
-        const bool invalid = S.effct < 1 && !S.late;
         if (tid == 0) {
-            if (invalid) {
-                if (lg) {
-                    lg->searched = S.converge; lg->effct = 0; lg->res_sum = 0.0; lg->valid = 0; lg->converged = S.converge;
-                    for (int i = 0; i < XLEN; i++) lg->x_after[i] = S.x[i];
-                }
-                S.iter++;
-                if (S.iter >= S.max_iter) S.done = 1;
-            } else {
-                S.error = S.late ? (S.late == 2 ? 3 : 2) : 1; S.done = 1;          // 2: a peer never delivered its sums; 3: the workers never reported; 1: singular system
+            if (lg && S.effct < 1 && !S.late) {
+                lg->searched = S.searched; lg->effct = 0; lg->res_sum = 0.0; lg->valid = 0; lg->converged = S.converge;
+                for (int i = 0; i < XLEN; i++) lg->x_after[i] = S.x[i];
             }
             S.n_pass++;
             ctl->iter = S.iter; ctl->n_pass = S.n_pass; ctl->done = S.done; ctl->error = S.error;
         }
         __syncthreads();
-        if (warp == 0) pub_publish(pub, tag_next, S.x, S.converge, S.done, lane);
         return;
     }
-    // ------------------------------------------------------------------ x_.boxplus(dx_) (:1817); on the last pass also the congruence at dx_ (:1836-1876)
+    // ------------------------------------------------------------------ after the publication
     const int finish = S.finish;
-    if (lane == 0) {
-        if (warp < 2) {
-            const int idx = warp == 0 ? 3 : 6, xo = warp == 0 ? X_ROT : X_OFFR;
-            const D3 d = d3(S.dxu[idx], S.dxu[idx + 1], S.dxu[idx + 2]);
-            stq(S.xnew + xo, qmul(ldq(S.x + xo), so3_exp(d)));                                      // SOn.hpp:233-236
-            if (finish) {
-                const M33 J = transpose33(A_matrix(d));
+    // [+] on the rest of the state; on the last pass also the congruence blocks at dx_ (:1836-1876)
+    if (warp == 1 && lane < 2 && finish) {
+        const int idx = lane == 0 ? 3 : 6;
+        const M33 J = transpose33(A_matrix(d3(S.dxu[idx], S.dxu[idx + 1], S.dxu[idx + 2])));
 #pragma unroll 1
-                for (int i = 0; i < 9; i++) S.J[warp][i] = J.m[i];
-            }
-        } else if (warp == 2) {
-            const D3 g = S2_boxplus(ld3(S.x + X_GRAV), S.dxu[21], S.dxu[22]);
-            st3(S.xnew + X_GRAV, g);
-            if (finish) S2_congruence(g, ld3(S.xprop + X_GRAV), S.dxu[21], S.dxu[22], S.M2);
-        }
+        for (int i = 0; i < 9; i++) S.J[lane][i] = J.m[i];
     }
-    if (warp == 3 && lane < 15) {
+    if (warp == 2 && lane == 0) {
+        const D3 g = S2_boxplus(ld3(S.x + X_GRAV), S.dxu[21], S.dxu[22]);                           // S2.hpp:136-142
+        st3(S.xnew + X_GRAV, g);
+        if (finish) S2_congruence(g, ld3(S.xprop + X_GRAV), S.dxu[21], S.dxu[22], S.M2);
+    }
+    if (warp == 3 && lane < 9) {
         const int b = lane / 3, c = lane % 3;
-        const int dof = b == 0 ? 0 : 9 + 3 * (b - 1);
-        const int xo = b == 0 ? X_POS : (b == 1 ? X_OFFT : (b == 2 ? X_VEL : (b == 3 ? X_BG : X_BA)));
-        S.xnew[xo + c] = S.x[xo + c] + S.dxu[dof + c];                                              // vect.hpp:117-119
-    }
-    __syncthreads();
-    if (tid == 0) ctl->prof[6] = clock64();
-    // ------------------------------------------------------------------ publish (warp 0 alone: no further block barrier on the path)
-    if (warp == 0) {
-        if (lane == 0) ctl->prof[10] = clock64();
-        pub_publish(pub, tag_next, S.xnew, S.converge, finish, lane);
-        if (lane == 0) ctl->prof[5] = clock64();
-    }
-    // ------------------------------------------------------------------ off the critical path
-    if (warp == 1) {
-        if (lane < XLEN) ctl->x[lane] = S.xnew[lane];
-        if (lane == 31) {
-            ctl->t = S.t; ctl->converge = S.converge; ctl->iter = S.iter + 1; ctl->n_pass = S.n_pass + 1; ctl->done = finish;
-        }
+        const int dof = 12 + 3 * b, xo = b == 0 ? X_VEL : (b == 1 ? X_BG : X_BA);
+        S.xnew[xo + c] = S.x[xo + c] + S.dxu[dof + c];
     }
     if (lg) {
-        if (tid < 144) lg->HtH[tid] = S.HTH[tid];
-        if (tid >= 160 && tid < 172) lg->Hth[tid - 160] = S.red[78 + tid - 160];
-        if (tid >= 192 && tid < 192 + XLEN) lg->x_after[tid - 192] = S.xnew[tid - 192];
+        if (tid >= 64 && tid < 64 + 144) lg->HtH[tid - 64] = S.HTH[tid - 64];
+        if (tid >= 224 && tid < 236) lg->Hth[tid - 224] = S.red[78 + tid - 224];
         if (tid == 255) { lg->searched = S.searched; lg->effct = S.effct; lg->res_sum = S.red[91]; lg->valid = 1; lg->converged = S.converge; }
     }
+    __syncthreads();
+    if (tid < XLEN) { ctl->x[tid] = S.xnew[tid]; if (lg) lg->x_after[tid] = S.xnew[tid]; }
+    if (tid == 32) { ctl->t = S.t; ctl->converge = S.converge; ctl->iter = S.iter + 1; ctl->n_pass = S.n_pass + 1; ctl->done = finish; }
     if (!finish) {
         // the reference leaves P_ = congruence-transformed P_propagated between passes
 #pragma unroll 1
@@ -628,8 +631,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
         } else {
             if (tid < PSTRIDE) S.red[tid] = tid < NRED ? a.red_g[tid] : 0.0;
             __syncthreads();
+            sol_expand(S);
         }
-        if (a.mode == 2) sol_exchange(S, a.p2p);
+        if (a.mode == 2) { sol_exchange(S, a.p2p); sol_expand(S); }
         if (tid == 0) ctl->prof[1] = clock64();
         sol_pass<EXTR>(S, ctl, a.logs, a.pub, pub_tag(a.nonce, p + 1));
         if (tid == 0) ctl->prof[7] = clock64();

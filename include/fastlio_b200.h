@@ -74,6 +74,15 @@ int fl_map_add_points(fl_map_t* m, const float* pts_xyzi, int n, int downsample_
 /* KD_TREE::Delete_Point_Boxes(vector<BoxPointType>&) -> int          ikd_Tree.cpp:632-658
  * boxes6: nb * (min xyz, max xyz); returns the number of points invalidated or an error (< 0) */
 int fl_map_delete_boxes(fl_map_t* m, const float* boxes6, int nb);
+/* KD_TREE::Add_Point_Boxes(vector<BoxPointType>&)                     ikd_Tree.cpp:576-603 (Add_by_range :854-934)
+ * points that Delete_Point_Boxes removed, lie in the boxes and have not been overwritten by later inserts come back
+ * (points removed by the down-sampling of Add_Points do not, as in the reference); returns how many, or an error (< 0) */
+int fl_map_add_boxes(fl_map_t* m, const float* boxes6, int nb);
+/* KD_TREE::acquire_removed_points(PointVector&)                       ikd_Tree.cpp:661-676 (called at laserMapping.cpp:225)
+ * the points removed by Delete_Point_Boxes since the previous call (the reference hands them over when it rebuilds the
+ * subtree, this map at once); the first call starts the record and returns 0.  Returns the number of points (writes at
+ * most cap of them), or an error (< 0).  Call with cap >= the return value of the deletes since the last call. */
+int fl_map_acquire_removed(fl_map_t* m, float* out_xyzi, int cap);
 /* KD_TREE::flatten(Root_Node, Storage, NOT_RECORD): all valid points  ikd_Tree.cpp:1627-1658
  * returns the number of valid points (writes at most cap of them) or an error (< 0) */
 int fl_map_flatten(fl_map_t* m, float* out_xyzi, int cap);

@@ -23,10 +23,20 @@
 //   Box_Search / Radius_Search               host filter over fl_map_flatten (compat only; never
 //                                            called by laserMapping.cpp)
 //   Delete_Points(PointVector&)              fl_map_delete_boxes with 2e-6 m boxes (same_point EPSS)
-//   Add_Point_Boxes                          unsupported (deleted points are not retained); no-op
-//   acquire_removed_points                   returns nothing (history of removed points is not kept)
+//   Add_Point_Boxes(vector<Box>&)            fl_map_add_boxes: box-deleted points not yet overwritten come back
+//   acquire_removed_points(PointVector&)     fl_map_acquire_removed: the points removed by Delete_Point_Boxes since the last call
+//                                            (the reference hands them over when it rebuilds the subtree; here at once)
 //   Root_Node                                non-null once built (laserMapping.cpp:909 tests it)
+//
+// Limits and failure reporting (the reference's members return void / int and cannot fail):
+//   * k_nearest <= 5 (NUM_MATCH_POINTS, include/common_lib.h:26 -- the only k FAST-LIO uses).  A larger k is an error:
+//     the call prints a diagnostic once, returns no neighbours and sets failed().
+//   * the CUDA device is chosen by KD_TREE::set_default_device(i) before construction, else by the environment variable
+//     FASTLIO_B200_DEVICE, else device 0 (the reference's tree is a global object, laserMapping.cpp:120).
+//   * ok() tells whether the device map exists (no GPU / out of memory at construction); failed() whether any call on
+//     this object has failed since clear_failed(); last_error() returns the library's message.
 #pragma once
+#include <stdlib.h>
 #include <math.h>
 #include <stdio.h>
 
@@ -54,11 +64,22 @@ public:
 
     KD_TREE(float delete_param = 0.5, float balance_param = 0.6, float box_length = 0.2) : downsample_size_(box_length) {
         (void)delete_param; (void)balance_param;
-        if (fl_map_create(&map_, 0, box_length) != FL_OK) {
-            fprintf(stderr, "KD_TREE(B200): %s\n", fl_last_error());
+        int dev = default_device();
+        if (dev < 0) { const char* e = getenv("FASTLIO_B200_DEVICE"); dev = e ? atoi(e) : 0; }
+        device_ = dev;
+        if (fl_map_create(&map_, dev, box_length) != FL_OK) {
+            fprintf(stderr, "KD_TREE(B200): cannot create the device map on CUDA device %d: %s\n", dev, fl_last_error());
             map_ = nullptr;
+            failed_ = true;
         }
     }
+    // extension: device selection and failure reporting (see the header comment)
+    static void set_default_device(int device) { default_device() = device; }
+    int device() const { return device_; }
+    bool ok() const { return map_ != nullptr; }
+    bool failed() const { return failed_; }
+    void clear_failed() { failed_ = false; }
+    static const char* last_error() { return fl_last_error(); }
     ~KD_TREE() { if (map_) fl_map_destroy(map_); }
     KD_TREE(const KD_TREE&) = delete;
     KD_TREE& operator=(const KD_TREE&) = delete;
@@ -85,7 +106,8 @@ public:
                         float max_dist = INFINITY) {
         Nearest_Points.clear();
         Point_Distance.clear();
-        const int k = std::min(k_nearest, 5);
+        if (!check_k(k_nearest)) return;
+        const int k = k_nearest;
         float q[4] = {point.x, point.y, point.z, 0.f};
         float pts[20], d2[5];
         int cnt = 0;
@@ -101,7 +123,10 @@ public:
     // extension: all queries in one launch (what a batched caller should use)
     void Nearest_Search_Batch(const PointVector& queries, int k_nearest, std::vector<PointVector>& out_points,
                               std::vector<std::vector<float>>& out_dist) {
-        const int nq = (int)queries.size(), k = std::min(k_nearest, 5);
+        out_points.clear();
+        out_dist.clear();
+        if (!check_k(k_nearest)) return;
+        const int nq = (int)queries.size(), k = k_nearest;
         std::vector<float> q, pts((size_t)nq * k * 4), d2((size_t)nq * k);
         std::vector<int> cnt(nq);
         pack(queries, q);
@@ -142,7 +167,14 @@ public:
         if (!PointToAdd.empty()) Root_Node = &root_token_;
         return rc;
     }
-    void Add_Point_Boxes(std::vector<BoxPointType>&) {}
+    void Add_Point_Boxes(std::vector<BoxPointType>& BoxPoints) {
+        std::vector<float> boxes;
+        for (const auto& b : BoxPoints) {
+            for (int a = 0; a < 3; a++) boxes.push_back(b.vertex_min[a]);
+            for (int a = 0; a < 3; a++) boxes.push_back(b.vertex_max[a]);
+        }
+        if (!boxes.empty()) check(std::min(0, fl_map_add_boxes(map_, boxes.data(), (int)BoxPoints.size())), "Add_Point_Boxes");
+    }
     void Delete_Points(PointVector& PointToDel) {
         std::vector<float> boxes;
         for (const auto& p : PointToDel) {
@@ -160,6 +192,7 @@ public:
         }
         int rc = fl_map_delete_boxes(map_, boxes.data(), (int)BoxPoints.size());
         if (rc < 0) { check(rc, "Delete_Point_Boxes"); return 0; }
+        removed_pending_ += rc;
         return rc;
     }
     void flatten(KD_TREE_NODE*, PointVector& Storage, delete_point_storage_set) {
@@ -169,7 +202,14 @@ public:
         if (got < 0) { check(got, "flatten"); return; }
         for (int i = 0; i < got; i++) Storage.push_back(unpack(&buf[(size_t)i * 4]));
     }
-    void acquire_removed_points(PointVector&) {}
+    void acquire_removed_points(PointVector& removed_points) {
+        // history of the points Delete_Point_Boxes removed since the previous call (the very first call starts the record)
+        std::vector<float> buf((size_t)std::max(removed_pending_, 1) * 4);
+        const int n = fl_map_acquire_removed(map_, buf.data(), removed_pending_);
+        if (n < 0) { check(n, "acquire_removed_points"); return; }
+        for (int i = 0; i < std::min(n, removed_pending_); i++) removed_points.push_back(unpack(&buf[(size_t)i * 4]));
+        removed_pending_ = 0;
+    }
     BoxPointType tree_range() {
         BoxPointType r;
         float b[6] = {0, 0, 0, 0, 0, 0};
@@ -200,10 +240,21 @@ private:
         set_intensity(p, f[3], 0);
         return p;
     }
-    static int check(int rc, const char* what) {
-        if (rc < 0) fprintf(stderr, "KD_TREE(B200)::%s failed: %s\n", what, fl_last_error());
+    int check(int rc, const char* what) {
+        if (rc < 0) { failed_ = true; fprintf(stderr, "KD_TREE(B200)::%s failed: %s\n", what, fl_last_error()); }
         return rc;
     }
+    bool check_k(int k) {
+        if (k >= 1 && k <= 5) return true;
+        failed_ = true;
+        static bool told = false;
+        if (!told) { told = true; fprintf(stderr, "KD_TREE(B200)::Nearest_Search: k_nearest = %d is not supported (1 <= k <= 5, NUM_MATCH_POINTS)\n", k); }
+        return false;
+    }
+    static int& default_device() { static int d = -1; return d; }
+    int device_ = 0;
+    int removed_pending_ = 0;      // points deleted by boxes since the last acquire_removed_points
+    bool failed_ = false;
     fl_map_t* map_ = nullptr;
     float downsample_size_;
     KD_TREE_NODE root_token_{0};

@@ -138,3 +138,45 @@ def test_stream_of_scans_matches_reference(problems):
         box = np.array([[c[0], -100, -10, c[0] + 6, 100, 30]], dtype=np.float32)
         assert g.Delete_Point_Boxes(box) == r.delete_boxes(box)
         check_same_map(g, r, make_batch(rng, pr.map_pts, 200))
+
+
+def test_acquire_removed_points_and_add_point_boxes(problems):
+    """a14 leftovers: acquire_removed_points (ikd_Tree.cpp:661-676) returns what Delete_Point_Boxes removed since the last call;
+    Add_Point_Boxes (ikd_Tree.cpp:576-603) brings box-deleted points back -- but not points removed by down-sampling."""
+    pr = problems("small")
+    rng = np.random.default_rng(41)
+    g = api.KdTree(0, 0.5); g.Build(pr.map_pts)
+    assert len(g.acquire_removed_points()) == 0                 # starts the record (laserMapping.cpp:273 asks before every delete)
+    before = sort_rows(g.flatten())
+    c = pr.map_pts[:, :3].mean(0)
+    boxes = np.array([[*(c - 6), *(c + 6)], [*(c + 8), *(c + 15)]], dtype=np.float32)
+    n_del = g.Delete_Point_Boxes(boxes)
+    assert n_del > 0
+    after = sort_rows(g.flatten())
+    removed = sort_rows(g.acquire_removed_points())
+    assert len(removed) == n_del and len(after) == len(before) - n_del
+    assert np.array_equal(sort_rows(np.concatenate([after, removed])), before)
+    assert len(g.acquire_removed_points()) == 0                 # handed over once
+    # down-sampling removes points too: those do not come back
+    batch = make_batch(rng, pr.map_pts, 1200, far_frac=0.0)
+    g.Add_Points(batch, True)
+    mid = sort_rows(g.flatten())
+    n_back = g.Add_Point_Boxes(boxes)
+    assert 0 < n_back <= n_del
+    now = sort_rows(g.flatten())
+    assert g.validnum() == len(now) == len(mid) + n_back
+    # every revived point is one of the removed ones, and the search sees them again
+    keyset = {tuple(r) for r in removed}
+    added_back = [r for r in now if tuple(r) in keyset]
+    assert len(added_back) == n_back
+    q = np.ascontiguousarray(np.array(added_back[:50], dtype=np.float32))
+    gp, gd, gc = g.Nearest_Search(q, 1)
+    assert (gd[:, 0] == 0).all()
+    if bind.have_ref():                                         # without intervening inserts the reference restores the map exactly
+        g2 = api.KdTree(0, 0.5); g2.Build(pr.map_pts)
+        g2.Delete_Point_Boxes(boxes)
+        assert g2.Add_Point_Boxes(boxes) == n_del
+        assert np.array_equal(sort_rows(g2.flatten()), before)
+        qq = make_batch(rng, pr.map_pts, 200)
+        r = bind.KdTree(pr.map_pts, "reference", downsample=0.5)
+        assert np.array_equal(g2.Nearest_Search(qq, 5)[1], r.knn(qq, 5)[1])

@@ -29,6 +29,7 @@ constexpr int PSTRIDE = 96;          // doubles per partial row (NRED = 92 padde
 // peer mailbox: [2 parities][P2P_MAX_RANKS slots][PSTRIDE values] x two tagged 8-byte words per value
 constexpr size_t P2P_MAIL_BYTES = sizeof(unsigned long long) * 2 * 2 * P2P_MAX_RANKS * PSTRIDE;
 constexpr int SEARCH_THREADS = 256;
+constexpr int SEARCH_C_THREADS = 64;
 constexpr int RESID_THREADS = 256;
 constexpr int MAX_LOGS = 16;
 
@@ -317,10 +318,9 @@ __device__ __forceinline__ void warp_accumulate(bool contrib, const double* h, d
 }
 
 // the search of one scan point by one warp, results stored as h_share_model leaves them (laserMapping.cpp:670-671)
-__device__ __forceinline__ void search_point(const MapView& m, const ScanView& sc, int q, float qx, float qy, float qz, bool use_cells, int lane) {
+__device__ __forceinline__ void search_point(const MapView& m, const ScanView& sc, int q, float qx, float qy, float qz, int lane) {
     KBest kb;
-    if (use_cells) knn_exact(m, qx, qy, qz, kb, lane);
-    else knn_query(m, qx, qy, qz, kb, lane);
+    knn_query(m, qx, qy, qz, kb, lane);
     float4 p;
     const int cnt = knn_fetch_warp(m, kb, p, lane);
     if (lane < KNN_K) sc.nearest[(size_t)q * KNN_K + lane] = p;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) k_search(MapView m, Scan
         const int cnt_chunk = min(32, wq1 - base);
         for (int l = 0; l < cnt_chunk; l++) {
             const float qx = __shfl_sync(FULL, wx, l), qy = __shfl_sync(FULL, wy, l), qz = __shfl_sync(FULL, wz, l);
-            search_point(m, sc, base + l, qx, qy, qz, false, lane);
+            search_point(m, sc, base + l, qx, qy, qz, lane);
         }
     }
 }
@@ -781,29 +781,31 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
     STAMP(7);
 }
 
-// k_search_c -- k_search with the map's hashed cell directory in front of the BVH walk (knn_exact, map.cuh): one warp per
-// scan point, one lane per neighbour cell.  Same neighbours, same distances, bit for bit.
-__global__ void __launch_bounds__(SEARCH_THREADS, 4) k_search_c(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
+// k_search_c -- the same search through the map's hashed cell directory: one LANE per scan point finds its cell's halo list (every
+// point of the 3x3x3 block of cells around it), scores it and proves its five neighbours exact; the few points it cannot prove
+// (nothing nearby, over-full cells) are walked through the BVH by the whole warp (knn_lanes, map.cuh).  Same neighbours, same
+// distances, bit for bit.
+__global__ void __launch_bounds__(SEARCH_C_THREADS) k_search_c(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
     pdl_wait();
     pdl_launch();
     if (ctl->done || !ctl->converge) return;
     const int lane = threadIdx.x & 31;
-    const int gwarp = (blockIdx.x * SEARCH_THREADS + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * SEARCH_THREADS) >> 5;
-    const long long nq = sc.q_end - sc.q_begin;
-    const int wq0 = sc.q_begin + (int)(nq * gwarp / nwarps);
-    const int wq1 = sc.q_begin + (int)(nq * (gwarp + 1) / nwarps);
-    for (int base = wq0; base < wq1; base += 32) {
-        const int myq = base + lane;
-        float wx = 0.f, wy = 0.f, wz = 0.f;
-        if (myq < wq1) {
-            const PoseS s = load_pose(ctl->x);
-            body_to_world(s, __ldg(&sc.body[myq]), wx, wy, wz);
-        }
-        const int cnt_chunk = min(32, wq1 - base);
-        for (int l = 0; l < cnt_chunk; l++)
-            search_point(m, sc, base + l, __shfl_sync(FULL, wx, l), __shfl_sync(FULL, wy, l), __shfl_sync(FULL, wz, l), true, lane);
+    const int q = sc.q_begin + blockIdx.x * SEARCH_C_THREADS + threadIdx.x;
+    const bool active = q < sc.q_end;
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    if (active) {
+        const PoseS s = load_pose(ctl->x);
+        body_to_world(s, __ldg(&sc.body[q]), wx, wy, wz);
     }
+    TBest kb;
+    knn_lanes(m, active, wx, wy, wz, kb, lane);
+    if (!active) return;
+    float4 p[KNN_K];
+    const int cnt = knn_fetch(m, kb, p);
+#pragma unroll
+    for (int j = 0; j < KNN_K; j++) sc.nearest[(size_t)q * KNN_K + j] = p[j];
+    sc.nearest_cnt[q] = cnt;
+    sc.selected[q] = (cnt < KNN_K) ? 0 : (kb.d[KNN_K - 1] > 5.0f ? 0 : 1);          // laserMapping.cpp:671
 }
 
 // k_residual -- everything of h_share_model after the search (laserMapping.cpp:674-752), one
@@ -1116,8 +1118,6 @@ int Filter::init() {
     else if (search_occ_ == 5) FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<5>, SEARCH_THREADS, 0));
     else FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search<4>, SEARCH_THREADS, 0));
     search_grid_max_ = sms_ * std::max(1, occ);
-    FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_search_c, SEARCH_THREADS, 0));
-    search_c_grid_max_ = sms_ * std::max(1, occ);
     if (const char* e = getenv("FASTLIO_B200_LEGACY")) fused_ = !(e[0] == '1');      // A/B: the split kernels of round 1
     FL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_update<false>, UPD_THREADS, 0));
     upd_capacity_[0] = sms_ * std::max(1, occ);
@@ -1287,8 +1287,8 @@ int Filter::launch_search_only() {
     const int nq = scan_.q_end - scan_.q_begin;
     if (fused()) return launch_update(1, 0, 1);
     if (search_mode_ == 1) {
-        const int cgrid = std::max(1, std::min(search_c_grid_max_, (nq * 32 + SEARCH_THREADS - 1) / SEARCH_THREADS));
-        FL_CUDA(launch_pdl(k_search_c, cgrid, SEARCH_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
+        const int cgrid = std::max(1, (nq + SEARCH_C_THREADS - 1) / SEARCH_C_THREADS);
+        FL_CUDA(launch_pdl(k_search_c, cgrid, SEARCH_C_THREADS, stream(), pdl_, map_->view(), scan_, (const FilterCtl*)ctl_.as<FilterCtl>()));
         return FL_OK;
     }
     const int sgrid = std::max(1, std::min(search_grid_max_, (nq * 32 + SEARCH_THREADS - 1) / SEARCH_THREADS));

@@ -134,7 +134,6 @@ private:
     DeviceBuffer mi_world_, mi_flag_add_, mi_flag_no_, mi_list_add_, mi_list_no_, mi_tmp_, mi_counts_;
     FilterCtl* h_ctl_ = nullptr;       // pinned staging
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
-    int search_c_grid_max_ = 0;
     int sms_ = 0, search_grid_max_ = 0, max_resid_grid_ = 0, resid_grid_ = 1;
     bool fused_ = true;
     DeviceBuffer pub_;                 // k_update's publication block

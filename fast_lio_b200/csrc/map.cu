@@ -39,7 +39,7 @@ void DeviceBuffer::release() {
 
 // counters_ layout
 enum Counter { C_LEAF_USED = 0, C_DELETED, C_ADDED, C_GROUPS, C_NINSERT, C_TOMB, C_ERROR, C_COMPACT,
-               C_DIR_CELLS, C_DIR_EXT, C_DIR_CROWDED, C_DIR_ERROR, C_DIR_WALKED, C_REMOVED, C_REVIVED, C_COUNT = 16 };
+               C_DIR_CELLS, C_DIR_POOL, C_DIR_CROWDED, C_DIR_ERROR, C_DIR_WALKED, C_REMOVED, C_REVIVED, C_NSLOTS, C_COUNT = 16 };
 
 // ============================================================================= kernels
 // ----------------------------------------------------------------------------- k-d partition build
@@ -221,134 +221,142 @@ __global__ void k_refit_level(MapView m, int k) {
 }
 
 // ----------------------------------------------------------------------------- cell directory (map.cuh)
-// find the entry of `key`, claiming a free one if the cell is new; returns its table index
-__device__ __forceinline__ unsigned dir_claim(const CellDir& D, unsigned long long key, int* counters) {
+// find the entry of `key`, claiming a free one if the cell is new; returns its table index (0xffffffff: table full)
+__device__ __forceinline__ unsigned dir_claim(const CellDir& D, unsigned long long key, int* counters, bool* fresh = nullptr) {
     unsigned s = cell_slot(key, D.cap);
     for (unsigned probes = 0; probes < D.cap; probes++) {
         const unsigned long long old = atomicCAS(&D.tab[s].key, 0ull, key);
-        if (old == 0ull) { atomicAdd(&counters[C_DIR_CELLS], 1); return s; }
+        if (old == 0ull) { atomicAdd(&counters[C_DIR_CELLS], 1); if (fresh) *fresh = true; return s; }
         if (old == key) return s;
         s = (s + 1 == D.cap) ? 0u : s + 1;
     }
     atomicExch(&counters[C_DIR_ERROR], 1);      // table full (the host sizes it so that this cannot happen)
     return 0xffffffffu;
 }
-__device__ __forceinline__ unsigned long long point_cell_key(const CellDir& D, const float4& p) {
-    return cell_key(cell_coord(p.x, D.inv_cell), cell_coord(p.y, D.inv_cell), cell_coord(p.z, D.inv_cell));
+__device__ __forceinline__ unsigned dir_find(const CellDir& D, unsigned long long key) {
+    unsigned s = cell_slot(key, D.cap);
+    for (unsigned probes = 0; probes < D.cap; probes++) {
+        const unsigned long long k = D.tab[s].key;
+        if (k == key) return s;
+        if (k == 0ull) break;
+        s = (s + 1 == D.cap) ? 0u : s + 1;
+    }
+    return 0xffffffffu;
 }
-__device__ __forceinline__ int dir_alloc_ext(const CellDir& D, int* counters) {
-    const int b = atomicAdd(&counters[C_DIR_EXT], 1);
-    if (b >= D.ext_cap) { atomicExch(&counters[C_DIR_ERROR], 1); return -1; }
-    return b;
+// the 27 cells whose halo lists a point belongs to: neighbour t of its own cell
+__device__ __forceinline__ unsigned long long halo_key(const CellDir& D, const float4& p, int t) {
+    return cell_key(cell_coord(p.x, D.inv_cell) + t % 3 - 1, cell_coord(p.y, D.inv_cell) + (t / 3) % 3 - 1, cell_coord(p.z, D.inv_cell) + t / 9 - 1);
+}
+__device__ __forceinline__ bool same_cell(const CellDir& D, const float4& a, const float4& b) {
+    return cell_coord(a.x, D.inv_cell) == cell_coord(b.x, D.inv_cell) && cell_coord(a.y, D.inv_cell) == cell_coord(b.y, D.inv_cell) &&
+           cell_coord(a.z, D.inv_cell) == cell_coord(b.z, D.inv_cell);
 }
 
-// (re)build, three passes over the slots / the table so that no thread ever waits for another:
-//   1. every live slot claims its cell and counts itself;  2. cells with more than CELL_INLINE points get an external
-//   bucket, counts restart;  3. every live slot appends its index.
-__global__ void k_dir_count(MapView m, int n_leaf_used, int* counters) {
+// (re)list, three passes so that no thread ever waits for another:
+//   1. every live slot claims its 27 cells and counts itself in each (cnt_cap holds a plain count);
+//   2. every cell gets room for its count + 25 % (a multiple of 4 indices) out of the list pool, counts restart;
+//   3. every live slot appends its index to its 27 lists.
+__global__ void k_halo_count(MapView m, int n_leaf_used, int* counters) {
     const long long total = (long long)n_leaf_used * LEAF;
     for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
         const float4 p = m.pts[slot];
         if (!slot_valid(p)) continue;
-        const unsigned e = dir_claim(m.dir, point_cell_key(m.dir, p), counters);
-        if (e != 0xffffffffu) atomicAdd(&m.dir.tab[e].cnt, 1);
+#pragma unroll 1
+        for (int t = 0; t < 27; t++) {
+            const unsigned e = dir_claim(m.dir, halo_key(m.dir, p, t), counters);
+            if (e != 0xffffffffu) atomicAdd(&m.dir.tab[e].cnt_cap, 1u);
+        }
     }
 }
-__global__ void k_dir_alloc(MapView m, int* counters) {
+__global__ void k_halo_alloc(MapView m, int* counters) {
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < m.dir.cap; e += gridDim.x * blockDim.x) {
         CellEntry& E = m.dir.tab[e];
-#pragma unroll
-        for (int j = 0; j < CELL_INLINE; j++) E.idx[j] = -1;
         if (E.key == 0ull) continue;
-        if (E.cnt > CELL_MAX) atomicAdd(&counters[C_DIR_CROWDED], 1);
-        if (E.cnt > CELL_INLINE) E.ext = dir_alloc_ext(m.dir, counters) + 1;
-        E.cnt = 0;
+        const int cnt = (int)E.cnt_cap;
+        if (cnt > HALO_MAX) { E.start = -1; E.cnt_cap = 0u; atomicAdd(&counters[C_DIR_CROWDED], 1); continue; }
+        const int room = (cnt + max(8, cnt / 4) + 3) & ~3;
+        const int start = atomicAdd(&counters[C_DIR_POOL], room);
+        if (start + room > m.dir.lists_cap) { E.start = -1; E.cnt_cap = 0u; atomicExch(&counters[C_DIR_ERROR], 1); continue; }
+        E.start = start;
+        E.cnt_cap = (unsigned)room << 16;
     }
 }
-__global__ void k_dir_fill(MapView m, int n_leaf_used) {
+__global__ void k_halo_fill(MapView m, int n_leaf_used) {
     const long long total = (long long)n_leaf_used * LEAF;
     for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < total; slot += (long long)gridDim.x * blockDim.x) {
         const float4 p = m.pts[slot];
         if (!slot_valid(p)) continue;
-        const unsigned long long key = point_cell_key(m.dir, p);
-        unsigned s = cell_slot(key, m.dir.cap);
-        unsigned probes = 0;
-        while (m.dir.tab[s].key != key && probes < m.dir.cap) { s = (s + 1 == m.dir.cap) ? 0u : s + 1; probes++; }       // present since pass 1
-        if (probes >= m.dir.cap) continue;
-        CellEntry& E = m.dir.tab[s];
-        const int pos = atomicAdd(&E.cnt, 1);
-        if (pos < CELL_INLINE) E.idx[pos] = (int)slot;
-        else if (pos < CELL_MAX && E.ext > 0) m.dir.ext[(size_t)(E.ext - 1) * CELL_EXT + pos - CELL_INLINE] = (int)slot;
-    }
-}
-// incremental: one thread (lane 0 of the inserting warp) lists a freshly written slot under its cell
-__device__ __forceinline__ void dir_add(const MapView& m, const float4& p, int slot, int* counters) {
-    const CellDir& D = m.dir;
-    const unsigned e = dir_claim(D, point_cell_key(D, p), counters);
-    if (e == 0xffffffffu) return;
-    CellEntry& E = D.tab[e];
-    const int pos = atomicAdd(&E.cnt, 1);
-    if (pos < CELL_INLINE) { *(volatile int*)&E.idx[pos] = slot; return; }
-    if (pos >= CELL_MAX) { if (pos == CELL_MAX) atomicAdd(&counters[C_DIR_CROWDED], 1); return; }
-    int x;
-    if (pos == CELL_INLINE) {                   // the fifth point of the cell brings the external bucket
-        x = dir_alloc_ext(D, counters) + 1;
-        if (x <= 0) return;                     // pool exhausted: the host grows the pool and re-lists the directory
-        atomicExch(&E.ext, x);
-    } else {
-        const long long t0 = clock64();
-        while ((x = atomicAdd(&E.ext, 0)) == 0) {       // published by the warp that appended the fifth point
-            if (atomicAdd(&counters[C_DIR_ERROR], 0) || clock64() - t0 > 200000000ll) { atomicExch(&counters[C_DIR_ERROR], 1); return; }
+#pragma unroll 1
+        for (int t = 0; t < 27; t++) {
+            const unsigned e = dir_find(m.dir, halo_key(m.dir, p, t));
+            if (e == 0xffffffffu) continue;
+            CellEntry& E = m.dir.tab[e];
+            if (E.start < 0) continue;
+            const unsigned old = atomicAdd(&E.cnt_cap, 1u);
+            const int pos = (int)(old & 0xffffu), room = (int)(old >> 16);
+            if (pos < room) m.dir.lists[E.start + pos] = (int)slot;
         }
     }
-    *(volatile int*)&D.ext[(size_t)(x - 1) * CELL_EXT + pos - CELL_INLINE] = slot;
 }
-// A slot is listed exactly once, under the cell of the point it holds.  When an insert re-uses the slot of a deleted point
-// (a tombstone keeps its listing: the search skips it by its flag), the listing stays if the new point falls into the same
-// cell; otherwise the old one is struck out (-1, skipped by the search, re-packed by the next re-list) and a new one added.
-__device__ __forceinline__ void dir_move(const MapView& m, bool was_tomb, const float4& old_p, const float4& p, int slot, int* counters) {
-    const CellDir& D = m.dir;
-    if (D.cap == 0u) return;
-    if (was_tomb) {
-        const unsigned long long ok = point_cell_key(D, old_p);
-        if (ok == point_cell_key(D, p)) return;
-        unsigned s = cell_slot(ok, D.cap);
-        for (unsigned probes = 0; probes < D.cap; probes++) {
-            const unsigned long long k = *(volatile unsigned long long*)&D.tab[s].key;
-            if (k == ok) {
-                CellEntry& E = D.tab[s];
-                const int seen = min(atomicAdd(&E.cnt, 0), CELL_MAX);
-                const int x = atomicAdd(&E.ext, 0);
-                for (int j = 0; j < seen; j++) {
-                    volatile int* at = j < CELL_INLINE ? (volatile int*)&E.idx[j] : (x > 0 ? (volatile int*)&D.ext[(size_t)(x - 1) * CELL_EXT + j - CELL_INLINE] : nullptr);
-                    if (at && *at == slot) { *at = -1; break; }
-                }
-                break;
-            }
-            if (k == 0ull) break;
-            s = (s + 1 == D.cap) ? 0u : s + 1;
+// incremental, two kernels (claim, then append) so that nobody waits for a list that is still being set up.
+// One warp per inserted point, lane t < 27 its t-th cell.  slots[i] < 0: the point re-used the slot of a deleted point of its own
+// cell -- all 27 listings are already in place.
+__global__ void __launch_bounds__(256) k_halo_claim(MapView m, const float4* __restrict__ pts, const int* __restrict__ slots, int n, int* counters) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        if (slots[i] < 0 || lane >= 27) continue;
+        bool fresh = false;
+        const unsigned e = dir_claim(m.dir, halo_key(m.dir, pts[i], lane), counters, &fresh);
+        if (e == 0xffffffffu || !fresh) continue;
+        CellEntry& E = m.dir.tab[e];
+        const int start = atomicAdd(&counters[C_DIR_POOL], HALO_NEW_CAP);
+        if (start + HALO_NEW_CAP > m.dir.lists_cap) { E.start = -1; E.cnt_cap = 0u; atomicExch(&counters[C_DIR_ERROR], 1); continue; }
+        E.start = start;
+        E.cnt_cap = (unsigned)HALO_NEW_CAP << 16;
+    }
+}
+__global__ void __launch_bounds__(256) k_halo_append(MapView m, const float4* __restrict__ pts, const int* __restrict__ slots, int n, int* counters) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const int slot = slots[i];
+        if (slot < 0 || lane >= 27) continue;
+        const unsigned e = dir_find(m.dir, halo_key(m.dir, pts[i], lane));
+        if (e == 0xffffffffu) { atomicExch(&counters[C_DIR_ERROR], 1); continue; }
+        CellEntry& E = m.dir.tab[e];
+        if (E.start < 0) continue;                                   // already over-full
+        const unsigned old = atomicAdd(&E.cnt_cap, 1u);
+        const int pos = (int)(old & 0xffffu), room = (int)(old >> 16);
+        if (pos < room) m.dir.lists[E.start + pos] = slot;
+        else {                                                       // no room: the cell is answered by the BVH walk until the next re-list
+            atomicSub(&E.cnt_cap, 1u);
+            if (atomicExch(&E.start, -1) >= 0) atomicAdd(&counters[C_DIR_CROWDED], 1);
         }
     }
-    dir_add(m, p, slot, counters);
 }
 
-// Batched Nearest_Search: one warp per query (cell directory, BVH walk for what that cannot prove).
-__global__ void __launch_bounds__(256) k_knn_batch(MapView m, const float4* __restrict__ q, int nq, int k,
+// Batched Nearest_Search: one lane per query (cell directory), BVH walk by the warp for what that cannot prove.
+__global__ void __launch_bounds__(128) k_knn_batch(MapView m, const float4* __restrict__ q, int nq, int k,
                                                     float4* __restrict__ out_pts, float* __restrict__ out_d2,
                                                     int* __restrict__ out_cnt) {
     const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += warps) {
-        const float4 qq = __ldg(&q[i]);
-        KBest kb;
-        knn_exact(m, qq.x, qq.y, qq.z, kb, lane);
-        float4 p;
-        const int cnt = min(k, knn_fetch_warp(m, kb, p, lane));
-        if (lane < k) {
-            out_pts[(size_t)i * k + lane] = p;
-            out_d2[(size_t)i * k + lane] = kb.d;
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < nq; base += stride) {
+        const int i = base + lane;
+        const bool active = i < nq;
+        float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) qq = __ldg(&q[i]);
+        TBest kb;
+        knn_lanes(m, active, qq.x, qq.y, qq.z, kb, lane);
+        if (!active) continue;
+        float4 p[KNN_K];
+        const int cnt = knn_fetch(m, kb, p);
+#pragma unroll
+        for (int j = 0; j < KNN_K; j++) {
+            if (j < k) { out_pts[(size_t)i * k + j] = p[j]; out_d2[(size_t)i * k + j] = kb.d[j]; }
         }
-        if (lane == 0) out_cnt[i] = cnt;
+        out_cnt[i] = min(k, cnt);
     }
 }
 
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(256) k_downsample_resolve(MapView m, const flo
 // One warp per new point: descend towards the nearest child box to the home leaf, claim a free slot there or
 // in its overflow chain (allocating a chain leaf from the pool if needed), publish the point
 // and grow the AABBs on the root path with float atomics ("partial refit").
-__global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restrict__ pts, int n, int* counters) {
+__global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restrict__ pts, int n, int* counters, int* __restrict__ slot_out) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
@@ -584,12 +592,12 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
         while (!placed) {
             const float4 cur = m.pts[leaf * LEAF + lane];
             const int w = __float_as_int(cur.w);
-            unsigned freem = __ballot_sync(FULL, w == SLOT_FREE || w == SLOT_TOMB || w == SLOT_TOMB_DS);
+            // free: never used, or the slot of a deleted point of the SAME cell (its 27 directory listings then serve the new point)
+            const bool tomb_ok = (w == SLOT_TOMB || w == SLOT_TOMB_DS) && (m.dir.cap == 0u || same_cell(m.dir, cur, p));
+            unsigned freem = __ballot_sync(FULL, w == SLOT_FREE || tomb_ok);
             while (freem && !placed) {
                 const int s = __ffs(freem) - 1;
-                // what lane s saw in the slot: a tombstone still carries the deleted point (and its directory listing)
                 const int seen = __shfl_sync(FULL, w, s);
-                const float ox = __shfl_sync(FULL, cur.x, s), oy = __shfl_sync(FULL, cur.y, s), oz = __shfl_sync(FULL, cur.z, s);
                 int old = 0;
                 if (lane == 0) old = atomicCAS((int*)&m.pts[leaf * LEAF + s].w, seen, SLOT_BUSY);
                 old = __shfl_sync(FULL, old, 0);
@@ -597,7 +605,7 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
                     if (lane == 0) {
                         m.payload[leaf * LEAF + s] = p.w;
                         m.pts[leaf * LEAF + s] = make_float4(p.x, p.y, p.z, __int_as_float(SLOT_VALID));
-                        dir_move(m, seen != SLOT_FREE, make_float4(ox, oy, oz, 0.f), p, leaf * LEAF + s, counters);
+                        slot_out[i] = seen == SLOT_FREE ? leaf * LEAF + s : -1;
                     }
                     placed = true;
                 } else {
@@ -621,7 +629,7 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
             if (nxt < 0) break;                                    // pool exhausted (host guarantees this cannot happen)
             leaf = nxt;
         }
-        if (!placed) continue;
+        if (!placed) { if (lane == 0) slot_out[i] = -1; continue; }
         // grow the boxes of the home leaf and of its ancestors
         int e = home;
         const float c3[3] = {p.x, p.y, p.z};
@@ -643,7 +651,7 @@ Map::Map(int device, float downsample_size) : device_(device), downsample_(downs
 
 Map::~Map() {
     cudaSetDevice(device_);
-    pts_.release(); payload_.release(); next_.release(); counters_.release(); dir_tab_.release(); dir_ext_.release(); removed_.release();
+    pts_.release(); payload_.release(); next_.release(); counters_.release(); dir_tab_.release(); dir_lists_.release(); removed_.release(); ins_slots_.release();
     for (int k = 0; k < MAX_LEVELS; k++) ebox_[k].release();
     segid_.release(); segtab_[0].release(); segtab_[1].release(); bbox_.release();
     src_.release(); keys_in_.release(); keys_out_.release(); vals_in_.release(); vals_out_.release();
@@ -767,43 +775,45 @@ int Map::build_from_sorted(const float4* d_src, int n) {
     return build_directory();
 }
 
-// (Re)build the cell directory over the live slots.  The table is sized from the point count and re-sized when the
-// cells turn out to be more numerous than guessed (load factor kept below ~0.6); the external-bucket pool likewise.
+// (Re)list the cell directory over the live slots.  Pass 1 counts into a table sized from the point count (re-sized when the
+// cells turn out to be more numerous than guessed: load factor below ~0.6); the list pool is then sized from the counts.
 int Map::build_directory() {
     FL_CUDA(cudaSetDevice(device_));
     if (!dir_enabled_) { v_.dir.cap = 0; return FL_OK; }
     const float cell = cell_override_ > 0.f ? cell_override_ : (downsample_ > 0.f ? 2.f * downsample_ : 1.f);
     const int used = h_counters_[C_LEAF_USED];
-    size_t want_cap = std::max<size_t>(dir_min_cap_, std::max<size_t>(8192, (size_t)n_valid_ + (size_t)n_valid_ / 4));
-    size_t want_ext = std::max<size_t>(dir_min_ext_, std::max<size_t>(4096, (size_t)n_valid_ / 4));
+    size_t want_cap = std::max<size_t>(dir_min_cap_, std::max<size_t>(16384, (size_t)n_valid_ * 4));
     int* d_cnt = counters_.as<int>();
+    const int nb = blocks_for((long long)used * LEAF, 256);
     for (int attempt = 0; attempt < 6; attempt++) {
         if (want_cap > 0xfffffff0ull / 2) { set_last_error("cell directory too large"); return FL_ERR_CAPACITY; }
         FL_CHECK(dir_tab_.reserve(sizeof(CellEntry) * want_cap));
-        FL_CHECK(dir_ext_.reserve(sizeof(int) * CELL_EXT * want_ext));
         v_.dir.tab = dir_tab_.as<CellEntry>();
-        v_.dir.ext = dir_ext_.as<int>();
         v_.dir.cap = (unsigned)(dir_tab_.bytes / sizeof(CellEntry));
-        v_.dir.ext_cap = (int)std::min<size_t>(dir_ext_.bytes / (sizeof(int) * CELL_EXT), 0x7fffffff);
         v_.dir.cell = cell;
         v_.dir.inv_cell = 1.0f / cell;
         v_.dir.n_walked = &d_cnt[C_DIR_WALKED];
         FL_CUDA(cudaMemsetAsync(dir_tab_.ptr, 0, sizeof(CellEntry) * (size_t)v_.dir.cap, stream_));
-        FL_CUDA(cudaMemsetAsync(dir_ext_.ptr, 0xff, sizeof(int) * CELL_EXT * (size_t)v_.dir.ext_cap, stream_));
-        FL_CUDA(cudaMemsetAsync(&d_cnt[C_DIR_CELLS], 0, sizeof(int) * 4, stream_));      // CELLS, EXT, CROWDED, ERROR
-        const int nb = blocks_for((long long)used * LEAF, 256);
-        k_dir_count<<<nb, 256, 0, stream_>>>(v_, used, d_cnt);
-        k_dir_alloc<<<blocks_for(v_.dir.cap, 256), 256, 0, stream_>>>(v_, d_cnt);
-        k_dir_fill<<<nb, 256, 0, stream_>>>(v_, used);
+        FL_CUDA(cudaMemsetAsync(&d_cnt[C_DIR_CELLS], 0, sizeof(int) * 4, stream_));      // CELLS, POOL, CROWDED, ERROR
+        k_halo_count<<<nb, 256, 0, stream_>>>(v_, used, d_cnt);
         FL_CUDA(cudaGetLastError());
         FL_CUDA(cudaMemcpyAsync(&h_counters_[C_DIR_CELLS], &d_cnt[C_DIR_CELLS], sizeof(int) * 4, cudaMemcpyDeviceToHost, stream_));
         FL_CUDA(cudaStreamSynchronize(stream_));
         const size_t cells = (size_t)h_counters_[C_DIR_CELLS];
-        const bool ext_short = h_counters_[C_DIR_ERROR] != 0;
-        const bool crowded_tab = cells * 10 > (size_t)v_.dir.cap * 6;
-        if (!ext_short && !crowded_tab) return FL_OK;
-        if (ext_short) want_ext = std::max<size_t>(want_ext * 2, (size_t)h_counters_[C_DIR_EXT] + 4096);
-        if (crowded_tab) want_cap = cells * 5 / 2 + 8192;
+        if (h_counters_[C_DIR_ERROR] || cells * 10 > (size_t)v_.dir.cap * 6) { want_cap = std::max(want_cap * 2, cells * 5 / 2 + 16384); continue; }
+        // lists: 27 listings per point + 25 % + 8 per cell (rounded to 4), plus room for the lists inserts will create
+        const size_t pool = (size_t)n_valid_ * 27 + (size_t)n_valid_ * 27 / 4 + cells * 12 + std::max<size_t>(dir_min_pool_, (size_t)HALO_NEW_CAP * 65536);
+        if (pool > 0x7ffffff0ull) { set_last_error("cell directory: list pool too large"); return FL_ERR_CAPACITY; }
+        FL_CHECK(dir_lists_.reserve(sizeof(int) * pool));
+        v_.dir.lists = dir_lists_.as<int>();
+        v_.dir.lists_cap = (int)std::min<size_t>(dir_lists_.bytes / sizeof(int), 0x7ffffff0ull);
+        k_halo_alloc<<<blocks_for(v_.dir.cap, 256), 256, 0, stream_>>>(v_, d_cnt);
+        k_halo_fill<<<nb, 256, 0, stream_>>>(v_, used);
+        FL_CUDA(cudaGetLastError());
+        FL_CUDA(cudaMemcpyAsync(&h_counters_[C_DIR_CELLS], &d_cnt[C_DIR_CELLS], sizeof(int) * 4, cudaMemcpyDeviceToHost, stream_));
+        FL_CUDA(cudaStreamSynchronize(stream_));
+        if (h_counters_[C_DIR_ERROR]) { dir_min_pool_ = std::max<size_t>(dir_min_pool_ * 2, (size_t)HALO_NEW_CAP * 262144); continue; }
+        return FL_OK;
     }
     set_last_error("cell directory: could not size the table");
     return FL_ERR_CAPACITY;
@@ -818,7 +828,7 @@ int Map::dir_stats(int* out6) const {
         cudaMemsetAsync(&counters_.as<int>()[C_DIR_WALKED], 0, sizeof(int), stream_);
         cudaStreamSynchronize(stream_);
     }
-    out6[0] = h_counters_[C_DIR_CELLS]; out6[1] = h_counters_[C_DIR_EXT]; out6[2] = h_counters_[C_DIR_CROWDED];
+    out6[0] = h_counters_[C_DIR_CELLS]; out6[1] = h_counters_[C_DIR_POOL]; out6[2] = h_counters_[C_DIR_CROWDED];
     out6[3] = (int)v_.dir.cap; out6[4] = n_dir_rebuilds_; out6[5] = v_.dir.cap ? walked : -1;
     return FL_OK;
 }
@@ -845,7 +855,7 @@ int Map::knn(const float* q_xyzi, int nq, int k, float* out_pts, float* out_d2, 
     char* base = scratch_.as<char>();
     float4* d_q = (float4*)base; float4* d_p = (float4*)(base + qb); float* d_d = (float*)(base + qb + pb); int* d_c = (int*)(base + qb + pb + db);
     FL_CUDA(cudaMemcpyAsync(d_q, q_xyzi, qb, cudaMemcpyHostToDevice, stream_));
-    k_knn_batch<<<blocks_for((long long)nq * 32, 256), 256, 0, stream_>>>(v_, d_q, nq, k, d_p, d_d, d_c);
+    k_knn_batch<<<blocks_for(nq, 128, 1 << 20), 128, 0, stream_>>>(v_, d_q, nq, k, d_p, d_d, d_c);
     FL_CUDA(cudaGetLastError());
     FL_CUDA(cudaMemcpyAsync(out_pts, d_p, pb, cudaMemcpyDeviceToHost, stream_));
     FL_CUDA(cudaMemcpyAsync(out_d2, d_d, db, cudaMemcpyDeviceToHost, stream_));
@@ -980,26 +990,35 @@ int Map::insert_device(const float4* d_pts, int n) {
         min_pool_ = std::max(min_pool_, n + 1024);
         FL_CHECK(rebuild());            // re-packs the leaves and re-sizes the pool
     }
-    if (v_.dir.cap) {       // room for n new cells and n new external buckets, so that the insert kernel can never run the table full
-        const size_t cells = (size_t)h_counters_[C_DIR_CELLS] + (size_t)n, ext = (size_t)h_counters_[C_DIR_EXT] + (size_t)n;
-        if (cells * 10 > (size_t)v_.dir.cap * 7 || ext > (size_t)v_.dir.ext_cap) {
-            dir_min_cap_ = std::max(dir_min_cap_, cells * 5 / 2 + 8192);
-            dir_min_ext_ = std::max(dir_min_ext_, ext + ext / 2 + 4096);
+    if (v_.dir.cap) {
+        // the insert kernels cope with a full table / an exhausted list pool (they flag it, the directory is re-listed below);
+        // re-list beforehand only when the table could get so full that probing degenerates
+        const size_t cells = (size_t)h_counters_[C_DIR_CELLS] + (size_t)n * 27;
+        if (cells * 10 > (size_t)v_.dir.cap * 9) {
+            dir_min_cap_ = std::max(dir_min_cap_, cells * 2 + 16384);
             n_dir_rebuilds_++;
             FL_CHECK(build_directory());
         }
     }
-    k_insert<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, n, counters_.as<int>());
+    FL_CHECK(ins_slots_.reserve(sizeof(int) * (size_t)n));
+    k_insert<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, n, counters_.as<int>(), ins_slots_.as<int>());
+    if (v_.dir.cap) {
+        k_halo_claim<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, ins_slots_.as<int>(), n, counters_.as<int>());
+        k_halo_append<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, ins_slots_.as<int>(), n, counters_.as<int>());
+    }
     FL_CUDA(cudaGetLastError());
     FL_CUDA(cudaMemcpyAsync(h_counters_, counters_.ptr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, stream_));
     FL_CUDA(cudaStreamSynchronize(stream_));
     if (h_counters_[C_ERROR]) { set_last_error("insert: overflow pool exhausted"); return FL_ERR_CAPACITY; }
     n_valid_ += n;
-    // directory: out of table room / external buckets, or too many crowded cells (stale entries pile up) -> re-list the live slots
+    // directory: out of room, or too many over-full cells (their queries walk the BVH) -> re-list the live slots
     if (v_.dir.cap) {
-        const bool full = (size_t)h_counters_[C_DIR_CELLS] * 10 > (size_t)v_.dir.cap * 7;
-        const bool crowded = h_counters_[C_DIR_CROWDED] > std::max(64, h_counters_[C_DIR_CELLS] / 64);
-        if (h_counters_[C_DIR_ERROR] || full || crowded) { n_dir_rebuilds_++; FL_CHECK(build_directory()); }
+        const bool crowded = h_counters_[C_DIR_CROWDED] > std::max(64, h_counters_[C_DIR_CELLS] / 128);
+        if (h_counters_[C_DIR_ERROR]) {
+            dir_min_cap_ = std::max(dir_min_cap_, (size_t)v_.dir.cap + (size_t)v_.dir.cap / 2);
+            dir_min_pool_ = std::max<size_t>(dir_min_pool_ * 2, (size_t)HALO_NEW_CAP * 262144);
+        }
+        if (h_counters_[C_DIR_ERROR] || crowded) { n_dir_rebuilds_++; FL_CHECK(build_directory()); }
     }
     return FL_OK;
 }

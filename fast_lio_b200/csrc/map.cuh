@@ -25,30 +25,29 @@
 namespace fl {
 
 // ----------------------------------------------------------------------------- cell directory
-// A hashed directory of cubic cells over the SAME leaf slots: cell (ix, iy, iz) = floor(p * inv_cell) lists the slot
-// indices of the points that were inserted into it.  It is the fast path of the k-NN search (one THREAD per query looks
-// at the 27 cells around it and proves the result exact from the distance to the faces of that block); whatever it
-// cannot prove -- sparse surroundings, crowded cells -- goes through the warp-cooperative BVH walk below, so the result
-// is always the exact answer of KD_TREE::Nearest_Search (ikd_Tree.cpp:426-461).  Validity lives in the slot's flag
-// only (a deleted point is skipped, nothing to update here); a slot re-used by a later insert may leave a stale index
-// behind, which the membership test of the scan rejects.
-constexpr int CELL_INLINE = 4;                     // slot indices stored in the directory entry itself (same 32-byte sector as the key)
-constexpr int CELL_EXT = 16;                       // further indices in the cell's external bucket (64 B)
-constexpr int CELL_MAX = CELL_INLINE + CELL_EXT;   // a cell listing more than this sends its queries to the BVH walk
+// A hashed directory of cubic cells over the SAME leaf slots, arranged so that a k-NN query is ONE look-up: the entry of cell
+// (ix, iy, iz) = floor(p * inv_cell) lists the slot indices of every point that lies in the 3x3x3 block of cells around it
+// (its "halo list", contiguous in HBM).  A thread finds its query's cell, scores the listed points and proves the result exact
+// from the distance to the faces of that block; whatever it cannot prove -- nothing nearby, an over-full cell -- goes through the
+// warp-cooperative BVH walk below, so the result is always the exact answer of KD_TREE::Nearest_Search (ikd_Tree.cpp:426-461).
+// Every point is listed in the 27 cells around it (HBM is plentiful: ~130 bytes of directory per point).  Validity lives in the
+// slot's flag only: a deleted point keeps its listings and is skipped; a slot is re-used only by a point of the SAME cell, whose
+// 27 listings are then still right.
 constexpr int CELL_OFF = 1 << 20;                  // 21 bits per axis
 constexpr int CELL_CLAMP = (1 << 20) - 4;
+constexpr int HALO_MAX = 2048;                     // a cell whose block holds more points than this sends its queries to the BVH walk
+constexpr int HALO_NEW_CAP = 48;                   // room of a list created by an insert (lists made by a re-list get count + 25 %)
 
-struct __align__(32) CellEntry {
+struct __align__(16) CellEntry {
     unsigned long long key;      // 0 = free, else cell_key()
-    int ext;                     // external bucket index + 1 (0 = none yet)
-    int cnt;                     // indices appended so far (may exceed CELL_MAX: overflow)
-    int idx[CELL_INLINE];
+    int start;                   // first index of the list in `lists` (multiple of 4); < 0: over-full, use the BVH walk
+    unsigned cnt_cap;            // low 16 bits: points listed, high 16 bits: room
 };
 struct CellDir {
     CellEntry* tab;              // [cap]
-    int* ext;                    // [ext_cap * CELL_EXT]
+    int* lists;                  // [lists_cap]
     unsigned cap;                // 0: directory disabled
-    int ext_cap;
+    int lists_cap;
     float cell, inv_cell;
     int* n_walked;               // statistics: queries that went through the BVH walk
 };
@@ -268,17 +267,15 @@ __device__ __forceinline__ void box_query(const MapView& m, const float* bmin, c
 }  // namespace fl
 
 // ============================================================================= cell directory: search
-// One WARP per query, one LANE per neighbour cell:
-//   1. lane t < 27 probes cell (own cell, faces, edges, corners -- nearest first) of the 3x3x3 block around the query:
-//      27 independent hashed look-ups in one step;
-//   2. the points the 27 cells list are numbered consecutively across the lanes (prefix sum of the counts) and scored 32 at a
-//      time, one candidate per lane -- a "virtual leaf" -- with the same k-best machinery as the BVH walk (knn_leaf);
-//      candidates of a cell whose nearest face is not closer than the current k-th best are not even loaded;
-//   3. every point OUTSIDE the block is at least g = (distance from the query to the block's faces) away, so the k best
-//      found are final when the k-th squared distance is strictly below g^2 (strict: the reference keeps the first of two
+// One THREAD per query:
+//   1. one hashed look-up finds the entry of the query's cell;
+//   2. the points of its halo list (everything in the 3x3x3 block of cells around the query) are scored four at a time, loads
+//      first; the k best are kept in registers;
+//   3. every point OUTSIDE the block is at least g = (distance from the query to the block's faces) away, so the k best found
+//      are final when the k-th squared distance is strictly below g^2 (strict: the reference keeps the first of two
 //      equidistant candidates, ikd_Tree.cpp:1088) -- tests/cell_directory_model.py pins the rule on the CPU.
-// Anything else (fewer than k points nearby, a crowded cell, coordinates beyond the key range) is NOT answered here: the
-// caller walks the BVH for that query (knn_query), so the result is always the exact answer of KD_TREE::Nearest_Search.
+// Anything else (no entry: nothing within a cell's width; fewer than k points; an over-full cell; coordinates beyond the key
+// range) is NOT answered here: knn_lanes() hands those queries to the warp-cooperative BVH walk (knn_query), one at a time.
 // Squared distances use the same explicitly rounded float32 arithmetic as the BVH walk (sq_dist3): either route returns
 // bit-identical distances.  All margins shrink the proven radius, never the searched set.
 namespace fl {
@@ -296,140 +293,148 @@ __device__ __forceinline__ unsigned cell_slot(unsigned long long key, unsigned c
     return __umulhi((unsigned)(h >> 32) ^ (unsigned)h, cap);
 }
 
-// absorb one candidate per lane (key = bits of its squared distance, INF_BITS for none; idx = its slot) into the k-best list
-__device__ __forceinline__ void kbest_absorb(KBest& kb, unsigned key, int idx, int lane) {
-    if (kb.n == 0) {
-        // empty list: the r-th smallest goes straight to lane r -- no merge
-        unsigned best = INF_BITS;
+struct TBest {                       // k best of one thread, ascending; empty entries: (+inf, -1)
+    float d[KNN_K];
+    int idx[KNN_K];
+    __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int r = 0; r < KNN_K; r++) {
-            best = __reduce_min_sync(FULL, key);
-            if (best == INF_BITS) break;
-            const int src = __ffs(__ballot_sync(FULL, key == best)) - 1;
-            const int bi = __shfl_sync(FULL, idx, src);
-            if (lane == r) { kb.d = __uint_as_float(best); kb.idx = bi; }
-            if (lane == src) key = INF_BITS;
-            kb.n = r + 1;
-        }
-        if (kb.n == KNN_K) kb.w = __uint_as_float(best);
-        return;
+        for (int i = 0; i < KNN_K; i++) { d[i] = INFINITY; idx[i] = -1; }
     }
-#pragma unroll 1
-    for (int it = 0; it < KNN_K; it++) {
-        const unsigned best = __reduce_min_sync(FULL, key);
-        if (best >= __float_as_uint(kb.w)) break;       // nothing strictly closer than the k-th best is left (covers the marker)
-        const int src = __ffs(__ballot_sync(FULL, key == best)) - 1;
-        kb.insert(__uint_as_float(best), __shfl_sync(FULL, idx, src), lane);
-        if (lane == src) key = INF_BITS;
+    __device__ __forceinline__ void insert(float nd, int nidx) {       // nd < d[K-1]; equal distances keep their arrival order
+#pragma unroll
+        for (int i = KNN_K - 1; i > 0; i--) {
+            const bool shift = nd < d[i - 1];
+            const bool here = !shift && nd < d[i];
+            d[i] = shift ? d[i - 1] : (here ? nd : d[i]);
+            idx[i] = shift ? idx[i - 1] : (here ? nidx : idx[i]);
+        }
+        if (nd < d[0]) { d[0] = nd; idx[0] = nidx; }
+    }
+};
+
+// one candidate (a deleted point keeps its listings: it is skipped by its flag)
+__device__ __forceinline__ void cell_consider(const float4& p, int idx, float qx, float qy, float qz, TBest& kb) {
+    if (slot_valid(p)) {
+        const float dd = sq_dist3(qx, qy, qz, p.x, p.y, p.z);
+        if (dd < kb.d[KNN_K - 1]) kb.insert(dd, idx);
     }
 }
 
-// Exact k-NN attempt for one query by one warp through the cell directory.  Returns true (warp-uniform) when kb is PROVEN
-// to be the exact answer; false: the caller must run knn_query().
-__device__ __forceinline__ bool cell_knn_warp(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
+// k-NN of one query by one thread.  Returns true when kb is PROVEN to be the exact answer.
+__device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, float qz, TBest& kb) {
     const CellDir& D = m.dir;
     kb.init();
     if (D.cap == 0u) return false;
     const float inv = D.inv_cell;
     const int ix = cell_coord(qx, inv), iy = cell_coord(qy, inv), iz = cell_coord(qz, inv);
     if (abs(ix) >= CELL_CLAMP - 1 || abs(iy) >= CELL_CLAMP - 1 || abs(iz) >= CELL_CLAMP - 1) return false;
+    // ---- 1. the entry of the query's cell
+    const unsigned long long key = cell_key(ix, iy, iz);
+    const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
+    unsigned s = cell_slot(key, D.cap);
+    uint4 e;
+    unsigned probes = 0;
+    while (true) {
+        e = __ldg(&tab[s]);
+        const unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+        if (k == key) break;
+        if (k == 0ull || ++probes >= D.cap) return false;             // no entry: no point within a cell's width of the query
+        s = (s + 1 == D.cap) ? 0u : s + 1;
+    }
+    const int start = (int)e.z, cnt = (int)(e.w & 0xffffu), room = (int)(e.w >> 16);
+    if (start < 0 || cnt > room) return false;                        // over-full
+    // ---- 2. the halo list, four candidates at a time (loads first)
+    const int4* list = reinterpret_cast<const int4*>(D.lists + start);
+#pragma unroll 1
+    for (int j = 0; j < cnt; j += 4) {
+        const int4 id = __ldg(&list[j >> 2]);
+        const int n4 = cnt - j;
+        float4 p0, p1, p2, p3;
+        p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);               // flag 0: not a live point
+        p0 = __ldg(&m.pts[id.x]);
+        if (n4 > 1) p1 = __ldg(&m.pts[id.y]);
+        if (n4 > 2) p2 = __ldg(&m.pts[id.z]);
+        if (n4 > 3) p3 = __ldg(&m.pts[id.w]);
+        cell_consider(p0, id.x, qx, qy, qz, kb);
+        cell_consider(p1, id.y, qx, qy, qz, kb);
+        cell_consider(p2, id.z, qx, qy, qz, kb);
+        cell_consider(p3, id.w, qx, qy, qz, kb);
+    }
+    if (kb.idx[KNN_K - 1] < 0) return false;
+    // ---- 3. proof: every point outside the 3x3x3 block is at least g away.  The distances from the query to the faces of its
+    // own cell are shrunk by more than any rounding of the cell arithmetic.
     const float c = D.cell;
-    // distance from the query to the low / high face of its own cell, shrunk by more than any rounding of the cell arithmetic
     const float marg = 4e-6f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 2.f * c);
-    const float lox = fmaxf(qx - (float)ix * c - marg, 0.f), hix = fmaxf((float)(ix + 1) * c - qx - marg, 0.f);
-    const float loy = fmaxf(qy - (float)iy * c - marg, 0.f), hiy = fmaxf((float)(iy + 1) * c - qy - marg, 0.f);
-    const float loz = fmaxf(qz - (float)iz * c - marg, 0.f), hiz = fmaxf((float)(iz + 1) * c - qz - marg, 0.f);
-    // ---- 1. this lane's cell: (dx, dy, dz) of entry `lane` of the nearest-first order, 6 bits each, ten per word
+    const float lox = qx - (float)ix * c, hix = (float)(ix + 1) * c - qx;
+    const float loy = qy - (float)iy * c, hiy = (float)(iy + 1) * c - qy;
+    const float loz = qz - (float)iz * c, hiz = (float)(iz + 1) * c - qz;
+    const float g = fmaxf(fminf(fminf(fminf(lox, hix), fminf(loy, hiy)), fminf(loz, hiz)) - marg, 0.f) + c - marg;
+    return kb.d[KNN_K - 1] < g * g;
+}
+
+// Exact k-NN for up to 32 queries of a warp (one per lane; `active` masks the tail).  The thread search answers what it
+// can prove; the rest goes through the cooperative BVH walk, one query at a time, and is handed back to its lane.
+__device__ __forceinline__ void knn_lanes(const MapView& m, bool active, float qx, float qy, float qz, TBest& kb, int lane) {
+    bool exact = true;
+    if (active) exact = cell_knn(m, qx, qy, qz, kb);
+    else kb.init();
+    unsigned todo = __ballot_sync(FULL, active && !exact);
+    if (todo && lane == 0 && m.dir.cap && m.dir.n_walked) atomicAdd(m.dir.n_walked, __popc(todo));
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float fx = __shfl_sync(FULL, qx, src), fy = __shfl_sync(FULL, qy, src), fz = __shfl_sync(FULL, qz, src);
+        KBest w;
+        knn_query(m, fx, fy, fz, w, lane);
+#pragma unroll
+        for (int j = 0; j < KNN_K; j++) {
+            const float dj = __shfl_sync(FULL, w.d, j);
+            const int ij = __shfl_sync(FULL, w.idx, j);
+            if (lane == src) { kb.d[j] = dj; kb.idx[j] = ij; }
+        }
+    }
+}
+
+// The neighbours as the caller sees them: coordinates + intensity, nearest first; candidates whose squared distances
+// differ by less than 1e-10 are ordered by x like PointType_CMP does for the reference's heap (ikd_Tree.h:102-108).
+__device__ __forceinline__ int knn_fetch(const MapView& m, TBest& kb, float4 (&p)[KNN_K]) {
     int cnt = 0;
-    unsigned ext = 0u;
-    uint4 b = make_uint4(0u, 0u, 0u, 0u);
-    float g2 = 0.f;                                   // squared distance from the query to this lane's cell
-    bool crowded = false;
-    if (lane < 27) {
-        const unsigned long long tbl = lane < 10 ? 0x498425159456515ull : (lane < 20 ? 0x292610661a411aull : 0x2a2a20a8220ull);
-        const unsigned code = (unsigned)(tbl >> (6 * (lane % 10))) & 63u;
-        const int dx = (int)(code & 3u) - 1, dy = (int)((code >> 2) & 3u) - 1, dz = (int)(code >> 4) - 1;
-        const float gx = dx < 0 ? lox : (dx > 0 ? hix : 0.f);
-        const float gy = dy < 0 ? loy : (dy > 0 ? hiy : 0.f);
-        const float gz = dz < 0 ? loz : (dz > 0 ? hiz : 0.f);
-        g2 = gx * gx + gy * gy + gz * gz;
-        const unsigned long long key = cell_key(ix + dx, iy + dy, iz + dz);
-        const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
-        unsigned s = cell_slot(key, D.cap);
-        for (unsigned probes = 0; probes < D.cap; probes++) {
-            const uint4 a = __ldg(&tab[2 * (size_t)s]);
-            const unsigned long long k = (unsigned long long)a.x | ((unsigned long long)a.y << 32);
-            if (k == key) {
-                cnt = (int)a.w; ext = a.z;
-                if (cnt > CELL_MAX || (cnt > CELL_INLINE && ext == 0u)) crowded = true;
-                else b = __ldg(&tab[2 * (size_t)s + 1]);
-                break;
+#pragma unroll
+    for (int j = 0; j < KNN_K; j++) {
+        p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kb.idx[j] >= 0) { p[j] = __ldg(&m.pts[kb.idx[j]]); p[j].w = __ldg(&m.payload[kb.idx[j]]); cnt++; }
+    }
+    bool tie = false;
+#pragma unroll
+    for (int j = 0; j + 1 < KNN_K; j++) tie |= kb.idx[j + 1] >= 0 && fabsf(kb.d[j + 1] - kb.d[j]) < 1e-10f;
+    if (tie) {
+#pragma unroll
+        for (int pass = 0; pass < KNN_K - 1; pass++) {
+#pragma unroll
+            for (int j = 0; j + 1 < KNN_K - pass; j++) {
+                if (kb.idx[j + 1] >= 0 && fabsf(kb.d[j + 1] - kb.d[j]) < 1e-10f && p[j + 1].x < p[j].x) {
+                    const float4 tp = p[j]; p[j] = p[j + 1]; p[j + 1] = tp;
+                    const float td = kb.d[j]; kb.d[j] = kb.d[j + 1]; kb.d[j + 1] = td;
+                    const int ti = kb.idx[j]; kb.idx[j] = kb.idx[j + 1]; kb.idx[j + 1] = ti;
+                }
             }
-            if (k == 0ull) break;
-            s = (s + 1 == D.cap) ? 0u : s + 1;
         }
     }
-    if (__any_sync(FULL, crowded)) return false;
-    // ---- 2. number the listed points across the lanes and score them 32 at a time
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-    const int total = __shfl_sync(FULL, incl, 31);
-    const int excl = incl - cnt;
-    for (int base = 0; base < total; base += 32) {
-        const int cand = base + lane;
-        // the cell of candidate `cand`: the last lane whose exclusive prefix is <= cand
-        int src = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const int probe = src + step;
-            const int e = __shfl_sync(FULL, excl, probe & 31);
-            if (probe < 32 && e <= cand) src = probe;
-        }
-        const int j = cand - __shfl_sync(FULL, excl, src);
-        const unsigned bx = __shfl_sync(FULL, b.x, src), by = __shfl_sync(FULL, b.y, src), bz = __shfl_sync(FULL, b.z, src), bw = __shfl_sync(FULL, b.w, src);
-        const unsigned se = __shfl_sync(FULL, ext, src);
-        const float sg2 = __shfl_sync(FULL, g2, src);
-        int idx = -1;
-        if (cand < total && sg2 < kb.w) {              // its cell can still matter
-            if (j < CELL_INLINE) idx = (int)(j == 0 ? bx : (j == 1 ? by : (j == 2 ? bz : bw)));
-            else idx = __ldg(&D.ext[(size_t)(se - 1u) * CELL_EXT + (j - CELL_INLINE)]);
-        }
-        unsigned key = INF_BITS;
-        if (idx >= 0) {                                 // struck-out listings are -1
-            const float4 p = __ldg(&m.pts[idx]);
-            if (slot_valid(p)) key = __float_as_uint(sq_dist3(qx, qy, qz, p.x, p.y, p.z));      // deleted points keep their listing
-        }
-        kbest_absorb(kb, key, idx, lane);
-    }
-    // ---- 3. proof
-    if (kb.n < KNN_K && __popc(__ballot_sync(FULL, lane < KNN_K && kb.idx >= 0)) < KNN_K) return false;
-    const float g = fminf(fminf(fminf(lox, hix), fminf(loy, hiy)), fminf(loz, hiz)) + c - marg;
-    return kb.w < g * g;
+    return cnt;
 }
 
-// exact k-NN of one query by one warp: the cell directory when it can prove its answer, else the BVH walk
-__device__ __forceinline__ void knn_exact(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
-    if (cell_knn_warp(m, qx, qy, qz, kb, lane)) return;
-    if (lane == 0 && m.dir.cap && m.dir.n_walked) atomicAdd(m.dir.n_walked, 1);
-    knn_query(m, qx, qy, qz, kb, lane);
-}
-
-// The neighbours as the caller sees them, warp-wide: lane j < K returns neighbour j (coordinates + intensity), nearest
-// first; candidates whose squared distances differ by less than 1e-10 are ordered by x like PointType_CMP does for the
-// reference's heap (ikd_Tree.h:102-108).  Returns the number of neighbours found.
+// the same for the warp-cooperative list of the BVH walk (lane j < K holds neighbour j)
 __device__ __forceinline__ int knn_fetch_warp(const MapView& m, KBest& kb, float4& p, int lane) {
     const bool have = lane < KNN_K && kb.idx >= 0;
     p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (have) { p = __ldg(&m.pts[kb.idx]); p.w = __ldg(&m.payload[kb.idx]); }
     const int cnt = __popc(__ballot_sync(FULL, have));
-    // ties: odd-even transposition over the (at most five) entries, only when some adjacent pair ties
     const float dn = __shfl_down_sync(FULL, kb.d, 1);
     const bool tie = lane + 1 < cnt && fabsf(dn - kb.d) < 1e-10f;
-    if (__any_sync(FULL, tie)) {
+    if (__any_sync(FULL, tie)) {                    // odd-even transposition over the (at most five) entries
 #pragma unroll
         for (int pass = 0; pass < KNN_K; pass++) {
-            const int partner = ((lane + pass) & 1) ? lane - 1 : lane + 1;           // pairs (0,1)(2,3) / (1,2)(3,4) alternately
+            const int partner = ((lane + pass) & 1) ? lane - 1 : lane + 1;
             const int pl = min(max(partner, 0), 31);
             const float od = __shfl_sync(FULL, kb.d, pl);
             const int oi = __shfl_sync(FULL, kb.idx, pl);

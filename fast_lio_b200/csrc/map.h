@@ -76,12 +76,12 @@ private:
     int n_valid_ = 0, n_tomb_ = 0, n_rebuilds_ = 0;
     bool built_ = false;
 
-    DeviceBuffer pts_, payload_, next_, counters_, dir_tab_, dir_ext_, removed_;
+    DeviceBuffer pts_, payload_, next_, counters_, dir_tab_, dir_lists_, removed_, ins_slots_;
     bool record_removed_ = false;
     int n_removed_ = 0;
     bool dir_enabled_ = true;
     float cell_override_ = 0.f;           // 0: cell edge = 2 x downsample size
-    size_t dir_min_cap_ = 0, dir_min_ext_ = 0;
+    size_t dir_min_cap_ = 0, dir_min_pool_ = 0;
     int n_dir_rebuilds_ = 0;
     DeviceBuffer ebox_[MAX_LEVELS];
     DeviceBuffer segid_, segtab_[2], bbox_;        // k-d partition build scratch

@@ -106,29 +106,48 @@ __device__ __forceinline__ void pub_publish(unsigned long long* pub, unsigned ta
 }
 
 // ============================================================================= workers
-// Everything of h_share_model after the search for one scan point (laserMapping.cpp:674-692), one thread per point; the
-// neighbours / the gate of a searching pass were stored by this very warp a moment ago (search_point).  Returns true when
+// Everything of h_share_model for one scan point (laserMapping.cpp:650-692), one lane per point.  Warp-collective (the search
+// hands the queries it cannot prove to the whole warp).  On a searching pass the five neighbours go from the search's registers
+// straight into the plane fit; they are stored once (map_incremental reads them, laserMapping.cpp:438-460).  Returns true when
 // the point contributes a row.
 template <bool EXTR>
-__device__ __forceinline__ bool measure_thread(const ScanView& sc, int q, const PoseS& s, const float4& pb, float wx, float wy, float wz,
-                                               bool searched, double* h, double& z, float& absres) {
-    if (!__ldcg(&sc.selected[q])) return false;                                                 // :674
-    float pabcd[4];
-    bool sel = true;
-    if (searched) {
-        float pn[KNN_K][3];
+__device__ __forceinline__ bool measure_fused(const MapView& m, const ScanView& sc, int q, bool active, const PoseS& s, bool searched,
+                                              bool search_only, int lane, double* h, double& z, float& absres) {
+    float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    if (active) {
+        pb = __ldg(&sc.body[q]);
+        body_to_world(s, pb, wx, wy, wz);                                   // :656-661
+    }
+    bool sel = false;
+    float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
+    if (searched) {                                                         // :667
+        TBest kb;
+        knn_lanes(m, active, wx, wy, wz, kb, lane);                         // :670
+        if (active) {
+            float4 p[KNN_K];
+            const int cnt = knn_fetch(m, kb, p);
 #pragma unroll
-        for (int j = 0; j < KNN_K; j++) { const float4 p = __ldcg(&sc.nearest[(size_t)q * KNN_K + j]); pn[j][0] = p.x; pn[j][1] = p.y; pn[j][2] = p.z; }
-        sel = esti_plane_dev(pabcd, pn, 0.1f);                                                  // :678
-        if (sel) sc.plane[q] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
-    } else {
+            for (int j = 0; j < KNN_K; j++) sc.nearest[(size_t)q * KNN_K + j] = p[j];
+            sc.nearest_cnt[q] = cnt;
+            sel = cnt >= KNN_K && !(kb.d[KNN_K - 1] > 5.0f);                // :671
+            if (search_only) { sc.selected[q] = sel ? 1 : 0; return false; }
+            if (sel) {
+                float pn[KNN_K][3];
+#pragma unroll
+                for (int j = 0; j < KNN_K; j++) { pn[j][0] = p[j].x; pn[j][1] = p[j].y; pn[j][2] = p[j].z; }
+                sel = esti_plane_dev(pabcd, pn, 0.1f);                      // :678
+                if (sel) sc.plane[q] = make_float4(pabcd[0], pabcd[1], pabcd[2], pabcd[3]);
+            }
+        }
+    } else if (active) {
         // a pass that does not search fits the plane to the SAME five neighbours (Nearest_Points persists, T3) and only
         // points whose fit and score succeeded last time are still selected: the fit is reused, not recomputed
-        const float4 pl = __ldcg(&sc.plane[q]);
-        pabcd[0] = pl.x; pabcd[1] = pl.y; pabcd[2] = pl.z; pabcd[3] = pl.w;
+        sel = sc.selected[q] != 0;                                          // :674
+        if (sel) { const float4 pl = sc.plane[q]; pabcd[0] = pl.x; pabcd[1] = pl.y; pabcd[2] = pl.z; pabcd[3] = pl.w; }
     }
     bool contrib = false;
-    if (sel) {
+    if (active && sel) {
         const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];             // :680
         const D3 p_body = d3(pb.x, pb.y, pb.z);
         const float score = (float)(1 - 0.9 * fabs((double)pd2) / sqrt(norm3(p_body)));        // :681 (T8)
@@ -138,7 +157,7 @@ __device__ __forceinline__ bool measure_thread(const ScanView& sc, int q, const 
             jacobian_row<EXTR>(s, pb, make_float4(pabcd[0], pabcd[1], pabcd[2], pd2), h, z);    // :723-751
         }
     }
-    if (!contrib) sc.selected[q] = 0;                                                           // :677 (stays 1 otherwise, :685)
+    if (active) sc.selected[q] = contrib ? 1 : 0;                                               // :677, :685
     return contrib;
 }
 
@@ -568,25 +587,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
             const int wq0 = a.sc.q_begin + (int)(nq * gwarp / nwarps), wq1 = a.sc.q_begin + (int)(nq * (gwarp + 1) / nwarps);
             for (int base = wq0; base < wq1; base += 32) {
                 const int q = base + lane;
-                const bool active = q < wq1;
-                float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-                float wx = 0.f, wy = 0.f, wz = 0.f;
-                if (active) {
-                    pb = __ldg(&a.sc.body[q]);
-                    body_to_world(s, pb, wx, wy, wz);                                       // laserMapping.cpp:656-661
-                }
-                if (searched) {                                                             // :667
-                    // one warp per point, one lane per neighbour cell (cell_knn_warp, map.cuh); BVH walk for what that cannot prove
-                    const int cnt_chunk = min(32, wq1 - base);
-                    for (int l = 0; l < cnt_chunk; l++)
-                        search_point(a.m, a.sc, base + l, __shfl_sync(FULL, wx, l), __shfl_sync(FULL, wy, l), __shfl_sync(FULL, wz, l), true, lane);
-                    __syncwarp();       // lanes 0..4 stored the neighbours and the gate; the owning lane reads them back below
-                }
-                if (a.search_only) continue;
                 double h[12]; double z = 0.0; float ar = 0.f;
-                bool contrib = false;
-                if (active) contrib = measure_thread<EXTR>(a.sc, q, s, pb, wx, wy, wz, searched, h, z, ar);
-                warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane, stage);
+                const bool contrib = measure_fused<EXTR>(a.m, a.sc, q, q < wq1, s, searched, a.search_only != 0, lane, h, z, ar);
+                if (!a.search_only) warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane, stage);
             }
             if (a.search_only) return;
 #pragma unroll

@@ -29,7 +29,7 @@ constexpr int PSTRIDE = 96;          // doubles per partial row (NRED = 92 padde
 // peer mailbox: [2 parities][P2P_MAX_RANKS slots][PSTRIDE values] x two tagged 8-byte words per value
 constexpr size_t P2P_MAIL_BYTES = sizeof(unsigned long long) * 2 * 2 * P2P_MAX_RANKS * PSTRIDE;
 constexpr int SEARCH_THREADS = 256;
-constexpr int SEARCH_C_THREADS = 64;
+constexpr int SEARCH_C_THREADS = 256;
 constexpr int RESID_THREADS = 256;
 constexpr int MAX_LOGS = 16;
 
@@ -786,10 +786,13 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
 // (nothing nearby, over-full cells) are walked through the BVH by the whole warp (knn_lanes, map.cuh).  Same neighbours, same
 // distances, bit for bit.
 __global__ void __launch_bounds__(SEARCH_C_THREADS) k_search_c(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
+    __shared__ WalkPool pool;
     pdl_wait();
     pdl_launch();
     if (ctl->done || !ctl->converge) return;
-    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) pool.n[0] = pool.n[1] = 0;
+    __syncthreads();
+    int phase = 0;
     const int q = sc.q_begin + blockIdx.x * SEARCH_C_THREADS + threadIdx.x;
     const bool active = q < sc.q_end;
     float wx = 0.f, wy = 0.f, wz = 0.f;
@@ -798,7 +801,7 @@ __global__ void __launch_bounds__(SEARCH_C_THREADS) k_search_c(MapView m, ScanVi
         body_to_world(s, __ldg(&sc.body[q]), wx, wy, wz);
     }
     TBest kb;
-    knn_lanes(m, active, wx, wy, wz, kb, lane);
+    knn_block(m, active, wx, wy, wz, kb, pool, phase);
     if (!active) return;
     float4 p[KNN_K];
     const int cnt = knn_fetch(m, kb, p);
@@ -1275,7 +1278,8 @@ int Filter::launch_update(int max_passes, int mode, int search_only) {
     { const char* e = getenv("FASTLIO_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
     const int cap = upd_capacity_[extrinsic_est_ ? 1 : 0];
     // every co-resident block works (a searching pass wants many warps in flight); small scans: at least 4 points per warp
-    int workers = mode == 3 ? 0 : std::min(cap - 1, (nq + 4 * UPD_WARPS - 1) / (4 * UPD_WARPS));
+    // one thread per point: full warps (the search is bound by a thread's own chain of loads, not by the number of SMs)
+    int workers = mode == 3 ? 0 : std::min(cap - 1, (nq + UPD_THREADS - 1) / UPD_THREADS);
     if (workers < 0) workers = 0;
     if (extrinsic_est_) FL_CUDA(launch_pdl(k_update<true>, workers + 1, UPD_THREADS, stream(), pdl_, a));
     else FL_CUDA(launch_pdl(k_update<false>, workers + 1, UPD_THREADS, stream(), pdl_, a));

@@ -340,23 +340,28 @@ __global__ void __launch_bounds__(256) k_halo_append(MapView m, const float4* __
 __global__ void __launch_bounds__(128) k_knn_batch(MapView m, const float4* __restrict__ q, int nq, int k,
                                                     float4* __restrict__ out_pts, float* __restrict__ out_d2,
                                                     int* __restrict__ out_cnt) {
-    const int lane = threadIdx.x & 31;
+    __shared__ WalkPool pool;
+    if (threadIdx.x == 0) pool.n[0] = pool.n[1] = 0;
+    __syncthreads();
+    int phase = 0;
     const int stride = gridDim.x * blockDim.x;
-    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < nq; base += stride) {
-        const int i = base + lane;
+    for (int base = blockIdx.x * blockDim.x; base < nq; base += stride) {          // block-uniform trip count (knn_block has barriers)
+        const int i = base + threadIdx.x;
         const bool active = i < nq;
         float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) qq = __ldg(&q[i]);
         TBest kb;
-        knn_lanes(m, active, qq.x, qq.y, qq.z, kb, lane);
-        if (!active) continue;
-        float4 p[KNN_K];
-        const int cnt = knn_fetch(m, kb, p);
+        knn_block(m, active, qq.x, qq.y, qq.z, kb, pool, phase);
+        if (active) {
+            float4 p[KNN_K];
+            const int cnt = knn_fetch(m, kb, p);
 #pragma unroll
-        for (int j = 0; j < KNN_K; j++) {
-            if (j < k) { out_pts[(size_t)i * k + j] = p[j]; out_d2[(size_t)i * k + j] = kb.d[j]; }
+            for (int j = 0; j < KNN_K; j++) {
+                if (j < k) { out_pts[(size_t)i * k + j] = p[j]; out_d2[(size_t)i * k + j] = kb.d[j]; }
+            }
+            out_cnt[i] = min(k, cnt);
         }
-        out_cnt[i] = min(k, cnt);
+        __syncthreads();
     }
 }
 

@@ -342,23 +342,39 @@ __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, f
         s = (s + 1 == D.cap) ? 0u : s + 1;
     }
     const int start = (int)e.z, cnt = (int)(e.w & 0xffffu), room = (int)(e.w >> 16);
-    if (start < 0 || cnt > room) return false;                        // over-full
-    // ---- 2. the halo list, four candidates at a time (loads first)
+    if (start < 0 || cnt > room || cnt <= 0) return false;            // over-full (or being set up)
+    // ---- 2. the halo list, eight candidates at a time: their point loads are issued together, and the indices of the next
+    // eight are fetched while these are scored (a scan is only a few warps per SM: the chain of dependent loads of one thread IS
+    // the run time -- probe, first indices, then one round trip per eight candidates)
     const int4* list = reinterpret_cast<const int4*>(D.lists + start);
+    const int nchunks = (cnt + 7) >> 3;
+    int4 ia = __ldg(&list[0]), ib = make_int4(0, 0, 0, 0);
+    if (cnt > 4) ib = __ldg(&list[1]);
 #pragma unroll 1
-    for (int j = 0; j < cnt; j += 4) {
-        const int4 id = __ldg(&list[j >> 2]);
-        const int n4 = cnt - j;
-        float4 p0, p1, p2, p3;
-        p0 = p1 = p2 = p3 = make_float4(0.f, 0.f, 0.f, 0.f);               // flag 0: not a live point
-        p0 = __ldg(&m.pts[id.x]);
-        if (n4 > 1) p1 = __ldg(&m.pts[id.y]);
-        if (n4 > 2) p2 = __ldg(&m.pts[id.z]);
-        if (n4 > 3) p3 = __ldg(&m.pts[id.w]);
-        cell_consider(p0, id.x, qx, qy, qz, kb);
-        cell_consider(p1, id.y, qx, qy, qz, kb);
-        cell_consider(p2, id.z, qx, qy, qz, kb);
-        cell_consider(p3, id.w, qx, qy, qz, kb);
+    for (int c = 0; c < nchunks; c++) {
+        const int n8 = cnt - 8 * c;                                            // candidates left, >= 1
+        float4 p0, p1, p2, p3, p4, p5, p6, p7;
+        p1 = p2 = p3 = p4 = p5 = p6 = p7 = make_float4(0.f, 0.f, 0.f, 0.f);  // flag 0: not a live point
+        p0 = __ldg(&m.pts[ia.x]);
+        if (n8 > 1) p1 = __ldg(&m.pts[ia.y]);
+        if (n8 > 2) p2 = __ldg(&m.pts[ia.z]);
+        if (n8 > 3) p3 = __ldg(&m.pts[ia.w]);
+        if (n8 > 4) p4 = __ldg(&m.pts[ib.x]);
+        if (n8 > 5) p5 = __ldg(&m.pts[ib.y]);
+        if (n8 > 6) p6 = __ldg(&m.pts[ib.z]);
+        if (n8 > 7) p7 = __ldg(&m.pts[ib.w]);
+        int4 na = ia, nb = ib;
+        if (n8 > 8) na = __ldg(&list[2 * c + 2]);
+        if (n8 > 12) nb = __ldg(&list[2 * c + 3]);
+        cell_consider(p0, ia.x, qx, qy, qz, kb);
+        cell_consider(p1, ia.y, qx, qy, qz, kb);
+        cell_consider(p2, ia.z, qx, qy, qz, kb);
+        cell_consider(p3, ia.w, qx, qy, qz, kb);
+        cell_consider(p4, ib.x, qx, qy, qz, kb);
+        cell_consider(p5, ib.y, qx, qy, qz, kb);
+        cell_consider(p6, ib.z, qx, qy, qz, kb);
+        cell_consider(p7, ib.w, qx, qy, qz, kb);
+        ia = na; ib = nb;
     }
     if (kb.idx[KNN_K - 1] < 0) return false;
     // ---- 3. proof: every point outside the 3x3x3 block is at least g away.  The distances from the query to the faces of its
@@ -372,20 +388,47 @@ __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, f
     return kb.d[KNN_K - 1] < g * g;
 }
 
-// Exact k-NN for up to 32 queries of a warp (one per lane; `active` masks the tail).  The thread search answers what it
-// can prove; the rest goes through the cooperative BVH walk, one query at a time, and is handed back to its lane.
-__device__ __forceinline__ void knn_lanes(const MapView& m, bool active, float qx, float qy, float qz, TBest& kb, int lane) {
+// Exact k-NN for the queries of a thread block (one per thread; `active` masks the tail).  The thread search answers what it can
+// prove.  The rest -- typically a handful of queries in sparse corners of the map, often neighbours in the scan and therefore
+// in the same warp -- is pooled in shared memory and walked through the BVH by ALL warps of the block, one query per warp at a
+// time (a cold walk is ~10 dependent memory round trips: five of them in one warp would make that warp the kernel's tail).
+// Block-wide: every thread of the block must call it (two barriers); `phase` is the caller's call counter (block-uniform,
+// starts at 0 with W.n[0] == W.n[1] == 0).
+constexpr int WALK_POOL = 64;
+struct WalkPool {
+    int n[2];                      // the counter of the current call and, being cleared, that of the next (see knn_block)
+    int who[WALK_POOL];
+    float x[WALK_POOL], y[WALK_POOL], z[WALK_POOL];
+    float rd[WALK_POOL][KNN_K];
+    int ri[WALK_POOL][KNN_K];
+};
+__device__ __forceinline__ void knn_block(const MapView& m, bool active, float qx, float qy, float qz, TBest& kb, WalkPool& W, int& phase) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     bool exact = true;
     if (active) exact = cell_knn(m, qx, qy, qz, kb);
     else kb.init();
-    unsigned todo = __ballot_sync(FULL, active && !exact);
-    if (todo && lane == 0 && m.dir.cap && m.dir.n_walked) atomicAdd(m.dir.n_walked, __popc(todo));
+    int mine = -1;
+    int* counter = &W.n[phase & 1];
+    if (active && !exact) {
+        mine = atomicAdd(counter, 1);
+        if (mine < WALK_POOL) { W.who[mine] = (int)threadIdx.x; W.x[mine] = qx; W.y[mine] = qy; W.z[mine] = qz; }
+    }
+    __syncthreads();
+    const int total = *counter, n = min(total, WALK_POOL);
+    if (threadIdx.x == 0) W.n[(phase + 1) & 1] = 0;     // nobody touches the other counter before the next call's first barrier
+    phase++;
+    for (int i = warp; i < n; i += nwarps) {
+        KBest w;
+        knn_query(m, W.x[i], W.y[i], W.z[i], w, lane);
+        if (lane < KNN_K) { W.rd[i][lane] = w.d; W.ri[i][lane] = w.idx; }
+    }
+    // more unproven queries than the pool holds (a scan far from the map): their own warp walks them
+    unsigned todo = __ballot_sync(FULL, mine >= WALK_POOL);
     while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
-        const float fx = __shfl_sync(FULL, qx, src), fy = __shfl_sync(FULL, qy, src), fz = __shfl_sync(FULL, qz, src);
         KBest w;
-        knn_query(m, fx, fy, fz, w, lane);
+        knn_query(m, __shfl_sync(FULL, qx, src), __shfl_sync(FULL, qy, src), __shfl_sync(FULL, qz, src), w, lane);
 #pragma unroll
         for (int j = 0; j < KNN_K; j++) {
             const float dj = __shfl_sync(FULL, w.d, j);
@@ -393,6 +436,12 @@ __device__ __forceinline__ void knn_lanes(const MapView& m, bool active, float q
             if (lane == src) { kb.d[j] = dj; kb.idx[j] = ij; }
         }
     }
+    __syncthreads();
+    if (mine >= 0 && mine < WALK_POOL) {
+#pragma unroll
+        for (int j = 0; j < KNN_K; j++) { kb.d[j] = W.rd[mine][j]; kb.idx[j] = W.ri[mine][j]; }
+    }
+    if (threadIdx.x == 0 && total && m.dir.cap && m.dir.n_walked) atomicAdd(m.dir.n_walked, total);
 }
 
 // The neighbours as the caller sees them: coordinates + intensity, nearest first; candidates whose squared distances

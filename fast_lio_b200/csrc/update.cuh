@@ -69,6 +69,7 @@ template <bool EXTR> struct WorkerSm {
     static constexpr int STAGE = 32 * RowStage<EXTR>::RS + 96;
     double stage[UPD_WARPS][STAGE];
     double wred[UPD_WARPS][PSTRIDE];
+    WalkPool walks;
     unsigned pose_bits[28];
     unsigned flags;
     int abort;
@@ -106,13 +107,13 @@ __device__ __forceinline__ void pub_publish(unsigned long long* pub, unsigned ta
 }
 
 // ============================================================================= workers
-// Everything of h_share_model for one scan point (laserMapping.cpp:650-692), one lane per point.  Warp-collective (the search
-// hands the queries it cannot prove to the whole warp).  On a searching pass the five neighbours go from the search's registers
+// Everything of h_share_model for one scan point (laserMapping.cpp:650-692), one thread per point.  Block-collective on a
+// searching pass (the queries the directory cannot prove are walked through the BVH by all warps of the block, knn_block).  On a searching pass the five neighbours go from the search's registers
 // straight into the plane fit; they are stored once (map_incremental reads them, laserMapping.cpp:438-460).  Returns true when
 // the point contributes a row.
 template <bool EXTR>
 __device__ __forceinline__ bool measure_fused(const MapView& m, const ScanView& sc, int q, bool active, const PoseS& s, bool searched,
-                                              bool search_only, int lane, double* h, double& z, float& absres) {
+                                              bool search_only, WalkPool& walks, int& phase, double* h, double& z, float& absres) {
     float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
     float wx = 0.f, wy = 0.f, wz = 0.f;
     if (active) {
@@ -123,7 +124,7 @@ __device__ __forceinline__ bool measure_fused(const MapView& m, const ScanView& 
     float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
     if (searched) {                                                         // :667
         TBest kb;
-        knn_lanes(m, active, wx, wy, wz, kb, lane);                         // :670
+        knn_block(m, active, wx, wy, wz, kb, walks, phase);                        // :670 (block-wide: two barriers)
         if (active) {
             float4 p[KNN_K];
             const int cnt = knn_fetch(m, kb, p);
@@ -540,7 +541,9 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
         // ------------------------------------------------------------------ worker block
         WorkerSm<EXTR>& Wk = *reinterpret_cast<WorkerSm<EXTR>*>(smem_raw);
         const int wb = (int)blockIdx.x - 1;
-        if (tid == 0) Wk.abort = 0;
+        if (tid == 0) { Wk.abort = 0; Wk.walks.n[0] = Wk.walks.n[1] = 0; }
+        __syncthreads();
+        int walk_phase = 0;
         for (int p = 0; p < a.max_passes; p++) {
             PoseS s;
             bool searched;
@@ -580,15 +583,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
             }
             double acc[3] = {0.0, 0.0, 0.0};
             double* stage = Wk.stage[warp];
-            // this warp's run of points: balanced over all worker warps, the same run every pass (a point's cached neighbours,
-            // plane and flag are only ever touched by its own warp)
-            const int nwarps = nwork * UPD_WARPS, gwarp = wb * UPD_WARPS + warp;
-            const long long nq = a.sc.q_end - a.sc.q_begin;
-            const int wq0 = a.sc.q_begin + (int)(nq * gwarp / nwarps), wq1 = a.sc.q_begin + (int)(nq * (gwarp + 1) / nwarps);
-            for (int base = wq0; base < wq1; base += 32) {
-                const int q = base + lane;
+            // tiles of UPD_THREADS consecutive points, dealt round-robin to the worker blocks -- the same tiles every pass (a point's
+            // cached neighbours, plane and flag are only ever touched by its own thread)
+            const int q0 = a.sc.q_begin, q1 = a.sc.q_end;
+            for (int tile = q0 + wb * UPD_THREADS; tile < q1; tile += nwork * UPD_THREADS) {
+                const int q = tile + tid;
                 double h[12]; double z = 0.0; float ar = 0.f;
-                const bool contrib = measure_fused<EXTR>(a.m, a.sc, q, q < wq1, s, searched, a.search_only != 0, lane, h, z, ar);
+                const bool contrib = measure_fused<EXTR>(a.m, a.sc, q, q < q1, s, searched, a.search_only != 0, Wk.walks, walk_phase, h, z, ar);
                 if (!a.search_only) warp_accumulate<EXTR>(contrib, h, z, ar, acc, lane, stage);
             }
             if (a.search_only) return;

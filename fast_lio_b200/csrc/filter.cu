@@ -212,6 +212,20 @@ __device__ __forceinline__ void jacobian_row(const PoseS& s, const float4& pb, c
     z = -(double)nv.w;
 }
 
+// the same with p_this = R_LI p_b + t_LI already at hand (body_to_world computes it on the way)
+template <bool EXTR>
+__device__ __forceinline__ void jacobian_row_at(const PoseS& s, const float4& pb, const D3& p_this, const float4& nv, double* h, double& z) {
+    D3 n = d3(nv.x, nv.y, nv.z);
+    D3 C = qrot(qconj(s.rot), n);
+    D3 A = mul33v(hat3(p_this), C);
+    h[0] = n.x; h[1] = n.y; h[2] = n.z; h[3] = A.x; h[4] = A.y; h[5] = A.z;
+    if (EXTR) {
+        D3 B = mul33v(mul33(hat3(d3(pb.x, pb.y, pb.z)), qmat(qconj(s.offR))), C);
+        h[6] = B.x; h[7] = B.y; h[8] = B.z; h[9] = C.x; h[10] = C.y; h[11] = C.z;
+    }
+    z = -(double)nv.w;
+}
+
 // Per-point part of h_share_model after the search (laserMapping.cpp:674-692).
 // Returns true when the point contributes a row.
 template <bool EXTR>
@@ -1088,7 +1102,7 @@ Filter::~Filter() {
     if (comm_ && nccl_) nccl_->CommDestroy(comm_);
     for (int r = 0; r < P2P_MAX_RANKS; r++) if (peer_ptr_[r]) cudaIpcCloseMemHandle(peer_ptr_[r]);
     mailbox_.release(); p2p_.release();
-    body_.release(); nearest_.release(); nearest_cnt_.release(); selected_.release(); normvec_.release(); plane_.release();
+    body_.release(); nearest_.release(); nearest_cnt_.release(); selected_.release(); normvec_.release(); plane_.release(); srange_.release();
     partials_.release(); red_.release(); ctl_.release(); ctl0_.release(); logs_.release(); pub_.release();
     mi_world_.release(); mi_flag_add_.release(); mi_flag_no_.release(); mi_list_add_.release(); mi_list_no_.release(); mi_tmp_.release(); mi_counts_.release();
     if (h_ctl_) cudaFreeHost(h_ctl_);
@@ -1145,6 +1159,8 @@ int Filter::reserve(int nq) {
     scan_.normvec = normvec_.as<float4>();
     FL_CHECK(plane_.reserve(sizeof(float4) * (size_t)nq));
     scan_.plane = plane_.as<float4>();
+    FL_CHECK(srange_.reserve(sizeof(double) * (size_t)nq));
+    scan_.srange = srange_.as<double>();
     return FL_OK;
 }
 

@@ -47,6 +47,7 @@ struct ScanView {
     unsigned char* selected; // [Q] point_selected_surf (persists across passes, trap T3)
     float4* normvec;         // [Q] (n, pd2)                                    normvec
     float4* plane;           // [Q] pabcd of the last search pass's plane fit (reused by the passes that do not search)
+    double* srange;          // [Q] sqrt(|p_body|) of the score (laserMapping.cpp:681), cached by the searching passes
     int q_begin, q_end;      // this rank's shard of the scan
     int Q;
 };
@@ -130,6 +131,7 @@ private:
     int search_occ_ = 5;               // resident k_search blocks per SM the kernel is compiled for
     int search_mode_ = 1;              // 1 (default): one lane per query through the cell directory (k_search_c); 0: one warp per query through the BVH (k_search)
     ScanView scan_;
+    DeviceBuffer srange_;
     DeviceBuffer body_, nearest_, nearest_cnt_, selected_, normvec_, plane_, partials_, red_, ctl_, ctl0_, logs_;
     DeviceBuffer mi_world_, mi_flag_add_, mi_flag_no_, mi_list_add_, mi_list_no_, mi_tmp_, mi_counts_;
     FilterCtl* h_ctl_ = nullptr;       // pinned staging

@@ -181,7 +181,8 @@ FL_COLD static double s2_theta_over_sin_exact(double v_sin2, double v_cos) {
     const double v_sin = sqrt(v_sin2);
     return atan2(v_sin, v_cos) / v_sin;
 }
-FL_HD void S2_boxminus(const D3& self, const D3& other, double& r0, double& r1) {   // S2.hpp:144-167
+// `Bo` = S2_Bx(other): the update calls this with other = x_propagated.grav, fixed for the whole update
+FL_HD void S2_boxminus_B(const D3& self, const D3& other, const double Bo[6], double& r0, double& r1) {   // S2.hpp:144-167
     const D3 cr = mul33v(hat3(self), other);
     const double v_sin2 = dot3(cr, cr);
     const double v_cos = dot3(self, other);
@@ -201,10 +202,13 @@ FL_HD void S2_boxminus(const D3& self, const D3& other, double& r0, double& r1) 
     } else {
         f = s2_theta_over_sin_exact(v_sin2, v_cos);
     }
-    double B[6]; S2_Bx(other, B);
     const D3 hv = mul33v(hat3(other), self);
-    r0 = f * (B[0] * hv.x + B[2] * hv.y + B[4] * hv.z);
-    r1 = f * (B[1] * hv.x + B[3] * hv.y + B[5] * hv.z);
+    r0 = f * (Bo[0] * hv.x + Bo[2] * hv.y + Bo[4] * hv.z);
+    r1 = f * (Bo[1] * hv.x + Bo[3] * hv.y + Bo[5] * hv.z);
+}
+FL_HD void S2_boxminus(const D3& self, const D3& other, double& r0, double& r1) {
+    double B[6]; S2_Bx(other, B);
+    S2_boxminus_B(self, other, B, r0, r1);
 }
 FL_HD void S2_Nx_yy(const D3& v, double N[6]) {                       // 2x3, S2.hpp:262-267
     double B[6]; S2_Bx(v, B);
@@ -214,29 +218,37 @@ FL_HD void S2_Nx_yy(const D3& v, double N[6]) {                       // 2x3, S2
         N[i * 3 + j] = 1 / S2_LEN / S2_LEN * s;
     }
 }
-FL_HD void S2_Mx(const D3& v, double d0, double d1, double M[6]) {    // 3x2, S2.hpp:269-281 (T4: exp(.., 1/2 == 0) is identity)
-    double B[6]; S2_Bx(v, B);
+// 3x2, S2.hpp:269-281.  T4: the reference's exp(.., scalar(1/2)) has scale 0 (integer division) -- the identity rotation: the
+// product with it is dropped here (E h == h exactly).  `B` = S2_Bx(v).
+FL_HD void S2_Mx_B(const D3& v, const double B[6], double d0, double d1, double M[6]) {
     M33 h = hat3(v);
     M33 T = h;
     if (!(sqrt(d0 * d0 + d1 * d1) < MTK_TOL)) {
         D3 Bu = d3(B[0] * d0 + B[1] * d1, B[2] * d0 + B[3] * d1, B[4] * d0 + B[5] * d1);
-        M33 E = qmat(mtk_exp(Bu, 0.0));
-        T = mul33(mul33(E, h), transpose33(A_matrix(Bu)));
+        T = mul33(h, transpose33(A_matrix(Bu)));
     }
     for (int i = 0; i < 3; i++) for (int j = 0; j < 2; j++) {
         double s = 0; for (int k = 0; k < 3; k++) s += T.m[i * 3 + k] * B[k * 2 + j];
         M[i * 2 + j] = -s;
     }
 }
-// 2x2 = Nx(x.grav) * Mx(x_prop.grav, delta)      (esekfom.hpp:1686-1690)
-FL_HD void S2_congruence(const D3& grav_now, const D3& grav_prop, double d0, double d1, double M2[4]) {
+FL_HD void S2_Mx(const D3& v, double d0, double d1, double M[6]) {
+    double B[6]; S2_Bx(v, B);
+    S2_Mx_B(v, B, d0, d1, M);
+}
+// 2x2 = Nx(x.grav) * Mx(x_prop.grav, delta)      (esekfom.hpp:1686-1690);  `Bp` = S2_Bx(grav_prop)
+FL_HD void S2_congruence_B(const D3& grav_now, const D3& grav_prop, const double Bp[6], double d0, double d1, double M2[4]) {
     double N[6], Mx[6];
     S2_Nx_yy(grav_now, N);
-    S2_Mx(grav_prop, d0, d1, Mx);
+    S2_Mx_B(grav_prop, Bp, d0, d1, Mx);
     for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) {
         double s = 0; for (int k = 0; k < 3; k++) s += N[i * 3 + k] * Mx[k * 2 + j];
         M2[i * 2 + j] = s;
     }
+}
+FL_HD void S2_congruence(const D3& grav_now, const D3& grav_prop, double d0, double d1, double M2[4]) {
+    double B[6]; S2_Bx(grav_prop, B);
+    S2_congruence_B(grav_now, grav_prop, B, d0, d1, M2);
 }
 
 // ---- compound state (build_manifold.hpp:192-200)

@@ -20,6 +20,8 @@
 // reduction (redux.sync) and the traversal state of each level lives in registers (the
 // recursion over the <= 7 levels is unrolled at compile time): no stack in memory.
 #pragma once
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace fl {
@@ -312,11 +314,70 @@ struct TBest {                       // k best of one thread, ascending; empty e
     }
 };
 
-// one candidate (a deleted point keeps its listings: it is skipped by its flag)
-__device__ __forceinline__ void cell_consider(const float4& p, int idx, float qx, float qy, float qz, TBest& kb) {
-    if (slot_valid(p)) {
-        const float dd = sq_dist3(qx, qy, qz, p.x, p.y, p.z);
-        if (dd < kb.d[KNN_K - 1]) kb.insert(dd, idx);
+// the entry of cell `key`: (start, cnt) of its halo list.  Returns 1: usable; 0: no entry (no point within a cell's width of
+// that cell); -1: over-full (or being set up) -- the BVH walk must answer
+__device__ __forceinline__ int cell_list(const CellDir& D, unsigned long long key, int& start, int& cnt) {
+    const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
+    unsigned s = cell_slot(key, D.cap);
+    uint4 e;
+    unsigned probes = 0;
+    while (true) {
+        e = __ldg(&tab[s]);
+        const unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
+        if (k == key) break;
+        if (k == 0ull || ++probes >= D.cap) return 0;
+        s = (s + 1 == D.cap) ? 0u : s + 1;
+    }
+    start = (int)e.z; cnt = (int)(e.w & 0xffffu);
+    const int room = (int)(e.w >> 16);
+    return (start >= 0 && cnt <= room && cnt > 0) ? 1 : -1;
+}
+
+// Score the halo list [start, start + cnt), eight candidates at a time: their point loads are issued together and the indices of
+// the next eight are fetched while these are scored (a scan is only a few warps per SM: the chain of dependent loads of one
+// thread IS the run time -- probe, first indices, then one round trip per eight candidates).
+// FILTER: accept only points whose cell coordinate on axis a equals want[a], for the axes with want[a] != INT_MIN (used by the
+// extension below, where a second list overlaps the first).
+template <bool FILTER>
+__device__ __forceinline__ void cell_scan_list(const MapView& m, int start, int cnt, float qx, float qy, float qz, TBest& kb,
+                                               int wantx, int wanty, int wantz) {
+    const int4* list = reinterpret_cast<const int4*>(m.dir.lists + start);
+    const float inv = m.dir.inv_cell;
+    const int nchunks = (cnt + 7) >> 3;
+    int4 ia = __ldg(&list[0]), ib = make_int4(0, 0, 0, 0);
+    if (cnt > 4) ib = __ldg(&list[1]);
+#pragma unroll 1
+    for (int c = 0; c < nchunks; c++) {
+        const int n8 = cnt - 8 * c;                                            // candidates left, >= 1
+        float4 p[8];
+#pragma unroll
+        for (int k = 1; k < 8; k++) p[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // flag 0: not a live point
+        p[0] = __ldg(&m.pts[ia.x]);
+        if (n8 > 1) p[1] = __ldg(&m.pts[ia.y]);
+        if (n8 > 2) p[2] = __ldg(&m.pts[ia.z]);
+        if (n8 > 3) p[3] = __ldg(&m.pts[ia.w]);
+        if (n8 > 4) p[4] = __ldg(&m.pts[ib.x]);
+        if (n8 > 5) p[5] = __ldg(&m.pts[ib.y]);
+        if (n8 > 6) p[6] = __ldg(&m.pts[ib.z]);
+        if (n8 > 7) p[7] = __ldg(&m.pts[ib.w]);
+        int4 na = ia, nb = ib;
+        if (n8 > 8) na = __ldg(&list[2 * c + 2]);
+        if (n8 > 12) nb = __ldg(&list[2 * c + 3]);
+        const int id[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            bool ok = slot_valid(p[k]);                                        // a deleted point keeps its listings: skipped by its flag
+            if (FILTER) {
+                if (wantx != INT_MIN) ok = ok && cell_coord(p[k].x, inv) == wantx;
+                if (wanty != INT_MIN) ok = ok && cell_coord(p[k].y, inv) == wanty;
+                if (wantz != INT_MIN) ok = ok && cell_coord(p[k].z, inv) == wantz;
+            }
+            if (ok) {
+                const float dd = sq_dist3(qx, qy, qz, p[k].x, p[k].y, p[k].z);
+                if (dd < kb.d[KNN_K - 1]) kb.insert(dd, id[k]);
+            }
+        }
+        ia = na; ib = nb;
     }
 }
 
@@ -327,64 +388,45 @@ __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, f
     if (D.cap == 0u) return false;
     const float inv = D.inv_cell;
     const int ix = cell_coord(qx, inv), iy = cell_coord(qy, inv), iz = cell_coord(qz, inv);
-    if (abs(ix) >= CELL_CLAMP - 1 || abs(iy) >= CELL_CLAMP - 1 || abs(iz) >= CELL_CLAMP - 1) return false;
-    // ---- 1. the entry of the query's cell
-    const unsigned long long key = cell_key(ix, iy, iz);
-    const uint4* tab = reinterpret_cast<const uint4*>(D.tab);
-    unsigned s = cell_slot(key, D.cap);
-    uint4 e;
-    unsigned probes = 0;
-    while (true) {
-        e = __ldg(&tab[s]);
-        const unsigned long long k = (unsigned long long)e.x | ((unsigned long long)e.y << 32);
-        if (k == key) break;
-        if (k == 0ull || ++probes >= D.cap) return false;             // no entry: no point within a cell's width of the query
-        s = (s + 1 == D.cap) ? 0u : s + 1;
-    }
-    const int start = (int)e.z, cnt = (int)(e.w & 0xffffu), room = (int)(e.w >> 16);
-    if (start < 0 || cnt > room || cnt <= 0) return false;            // over-full (or being set up)
-    // ---- 2. the halo list, eight candidates at a time: their point loads are issued together, and the indices of the next
-    // eight are fetched while these are scored (a scan is only a few warps per SM: the chain of dependent loads of one thread IS
-    // the run time -- probe, first indices, then one round trip per eight candidates)
-    const int4* list = reinterpret_cast<const int4*>(D.lists + start);
-    const int nchunks = (cnt + 7) >> 3;
-    int4 ia = __ldg(&list[0]), ib = make_int4(0, 0, 0, 0);
-    if (cnt > 4) ib = __ldg(&list[1]);
-#pragma unroll 1
-    for (int c = 0; c < nchunks; c++) {
-        const int n8 = cnt - 8 * c;                                            // candidates left, >= 1
-        float4 p0, p1, p2, p3, p4, p5, p6, p7;
-        p1 = p2 = p3 = p4 = p5 = p6 = p7 = make_float4(0.f, 0.f, 0.f, 0.f);  // flag 0: not a live point
-        p0 = __ldg(&m.pts[ia.x]);
-        if (n8 > 1) p1 = __ldg(&m.pts[ia.y]);
-        if (n8 > 2) p2 = __ldg(&m.pts[ia.z]);
-        if (n8 > 3) p3 = __ldg(&m.pts[ia.w]);
-        if (n8 > 4) p4 = __ldg(&m.pts[ib.x]);
-        if (n8 > 5) p5 = __ldg(&m.pts[ib.y]);
-        if (n8 > 6) p6 = __ldg(&m.pts[ib.z]);
-        if (n8 > 7) p7 = __ldg(&m.pts[ib.w]);
-        int4 na = ia, nb = ib;
-        if (n8 > 8) na = __ldg(&list[2 * c + 2]);
-        if (n8 > 12) nb = __ldg(&list[2 * c + 3]);
-        cell_consider(p0, ia.x, qx, qy, qz, kb);
-        cell_consider(p1, ia.y, qx, qy, qz, kb);
-        cell_consider(p2, ia.z, qx, qy, qz, kb);
-        cell_consider(p3, ia.w, qx, qy, qz, kb);
-        cell_consider(p4, ib.x, qx, qy, qz, kb);
-        cell_consider(p5, ib.y, qx, qy, qz, kb);
-        cell_consider(p6, ib.z, qx, qy, qz, kb);
-        cell_consider(p7, ib.w, qx, qy, qz, kb);
-        ia = na; ib = nb;
-    }
+    if (abs(ix) >= CELL_CLAMP - 2 || abs(iy) >= CELL_CLAMP - 2 || abs(iz) >= CELL_CLAMP - 2) return false;
+    // ---- 1. + 2. the halo list of the query's cell: every point of the 3x3x3 block of cells around it
+    int start, cnt;
+    if (cell_list(D, cell_key(ix, iy, iz), start, cnt) <= 0) return false;
+    cell_scan_list<false>(m, start, cnt, qx, qy, qz, kb, INT_MIN, INT_MIN, INT_MIN);
     if (kb.idx[KNN_K - 1] < 0) return false;
-    // ---- 3. proof: every point outside the 3x3x3 block is at least g away.  The distances from the query to the faces of its
-    // own cell are shrunk by more than any rounding of the cell arithmetic.
+    // ---- 3. proof: every point outside the block is at least g away.  The distances from the query to the faces of its own cell
+    // are shrunk by more than any rounding of the cell arithmetic.
     const float c = D.cell;
     const float marg = 4e-6f * (fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 2.f * c);
-    const float lox = qx - (float)ix * c, hix = (float)(ix + 1) * c - qx;
-    const float loy = qy - (float)iy * c, hiy = (float)(iy + 1) * c - qy;
-    const float loz = qz - (float)iz * c, hiz = (float)(iz + 1) * c - qz;
-    const float g = fmaxf(fminf(fminf(fminf(lox, hix), fminf(loy, hiy)), fminf(loz, hiz)) - marg, 0.f) + c - marg;
+    const float lox = fmaxf(qx - (float)ix * c - marg, 0.f), hix = fmaxf((float)(ix + 1) * c - qx - marg, 0.f);
+    const float loy = fmaxf(qy - (float)iy * c - marg, 0.f), hiy = fmaxf((float)(iy + 1) * c - qy - marg, 0.f);
+    const float loz = fmaxf(qz - (float)iz * c - marg, 0.f), hiz = fmaxf((float)(iz + 1) * c - qz - marg, 0.f);
+    const float c1 = c - marg;
+    float gx = fminf(lox, hix) + c1, gy = fminf(loy, hiy) + c1, gz = fminf(loz, hiz) + c1;      // distance to the block's nearest face, per axis
+    if (kb.d[KNN_K - 1] < fminf(fminf(gx, gy), gz) * fminf(fminf(gx, gy), gz)) return true;
+    // ---- 4. extension.  The block's nearest face is too close on some axes: on each of them grow the block by one slab of cells
+    // on that side.  The slab(s) are covered by the halo lists of the cells at offset e = (ex, ey, ez) (e_a = the side on a grown
+    // axis, 0 elsewhere) and of every combination with some components zeroed; a point is taken from the ONE list whose non-zero
+    // components are exactly the axes on which the point lies in the new slab, so nothing is scored twice.
+    const float w = kb.d[KNN_K - 1];
+    const int ex = gx * gx <= w ? (lox < hix ? -1 : 1) : 0;
+    const int ey = gy * gy <= w ? (loy < hiy ? -1 : 1) : 0;
+    const int ez = gz * gz <= w ? (loz < hiz ? -1 : 1) : 0;
+#pragma unroll 1
+    for (int combo = 1; combo < 8; combo++) {
+        const int dx = (combo & 1) ? ex : 0, dy = (combo & 2) ? ey : 0, dz = (combo & 4) ? ez : 0;
+        if (((combo & 1) && !ex) || ((combo & 2) && !ey) || ((combo & 4) && !ez)) continue;       // that axis is not grown
+        int st2, cn2;
+        const int have = cell_list(D, cell_key(ix + dx, iy + dy, iz + dz), st2, cn2);
+        if (have < 0) return false;
+        if (have == 0) continue;                // nothing within a cell's width of that cell: nothing to add
+        cell_scan_list<true>(m, st2, cn2, qx, qy, qz, kb, dx ? ix + 2 * dx : INT_MIN, dy ? iy + 2 * dy : INT_MIN, dz ? iz + 2 * dz : INT_MIN);
+    }
+    // the grown block: on a grown axis the far face of the new slab or the untouched opposite face, whichever is nearer
+    if (ex) gx = fminf(fminf(lox, hix) + c + c1, fmaxf(lox, hix) + c1);
+    if (ey) gy = fminf(fminf(loy, hiy) + c + c1, fmaxf(loy, hiy) + c1);
+    if (ez) gz = fminf(fminf(loz, hiz) + c + c1, fmaxf(loz, hiz) + c1);
+    const float g = fminf(fminf(gx, gy), gz);
     return kb.d[KNN_K - 1] < g * g;
 }
 

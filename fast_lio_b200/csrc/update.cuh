@@ -60,6 +60,7 @@ struct SolverSm {
     double x[XLEN], xprop[XLEN], xnew[XLEN];
     double dx[NDOF], dxn[NDOF], dxu[NDOF], limit[NDOF];
     double J[2][9], M2[4];
+    double Bprop[6];               // S2_Bx(x_propagated.grav): fixed for the update
     double R;
     int iter, t, converge, done, n_pass, max_iter, error;
     int effct, ok, finish, searched, late;
@@ -116,9 +117,12 @@ __device__ __forceinline__ bool measure_fused(const MapView& m, const ScanView& 
                                               bool search_only, WalkPool& walks, int& phase, double* h, double& z, float& absres) {
     float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
     float wx = 0.f, wy = 0.f, wz = 0.f;
+    D3 p_this = d3(0.0, 0.0, 0.0);
     if (active) {
         pb = __ldg(&sc.body[q]);
-        body_to_world(s, pb, wx, wy, wz);                                   // :656-661
+        p_this = qrot(s.offR, d3(pb.x, pb.y, pb.z)) + s.offT;               // :656-661 (also the lever arm of the Jacobian, :733)
+        const D3 g = qrot(s.rot, p_this) + s.pos;
+        wx = (float)g.x; wy = (float)g.y; wz = (float)g.z;
     }
     bool sel = false;
     float pabcd[4] = {0.f, 0.f, 0.f, 0.f};
@@ -150,12 +154,15 @@ __device__ __forceinline__ bool measure_fused(const MapView& m, const ScanView& 
     bool contrib = false;
     if (active && sel) {
         const float pd2 = pabcd[0] * wx + pabcd[1] * wy + pabcd[2] * wz + pabcd[3];             // :680
-        const D3 p_body = d3(pb.x, pb.y, pb.z);
-        const float score = (float)(1 - 0.9 * fabs((double)pd2) / sqrt(norm3(p_body)));        // :681 (T8)
+        // sqrt(p_body.norm()) depends on the point alone: computed on the searching passes, cached for the others
+        double srange;
+        if (searched) { srange = sqrt(norm3(d3(pb.x, pb.y, pb.z))); sc.srange[q] = srange; }
+        else srange = sc.srange[q];
+        const float score = (float)(1 - 0.9 * fabs((double)pd2) / srange);                     // :681 (T8)
         if ((double)score > 0.9) {                                                              // :683
             contrib = true;
             absres = fabsf(pd2);                                                                // res_last
-            jacobian_row<EXTR>(s, pb, make_float4(pabcd[0], pabcd[1], pabcd[2], pd2), h, z);    // :723-751
+            jacobian_row_at<EXTR>(s, pb, p_this, make_float4(pabcd[0], pabcd[1], pabcd[2], pd2), h, z);    // :723-751
         }
     }
     if (active) sc.selected[q] = contrib ? 1 : 0;                                               // :677, :685
@@ -175,6 +182,8 @@ __device__ void sol_load(SolverSm& S, const FilterCtl* ctl) {
         S.n_pass = __ldcg(&ctl->n_pass); S.max_iter = __ldcg(&ctl->max_iter); S.error = 0; S.late = 0;
     }
     __syncthreads();
+    if (tid == 0) S2_Bx(ld3(S.xprop + X_GRAV), S.Bprop);
+    __syncthreads();
 }
 
 // the state-only half of a pass (esekfom.hpp:1651-1699): dx = x [-] x_prop, dx_new, the congruence blocks, Pt = T P_prop T^T
@@ -193,8 +202,8 @@ __device__ void sol_prepare(SolverSm& S) {
             S.dxn[idx] = seg.x; S.dxn[idx + 1] = seg.y; S.dxn[idx + 2] = seg.z;
         } else if (warp == 2) {         // S2 block: grav (idx 21)
             double d0, d1;
-            S2_boxminus(ld3(S.x + X_GRAV), ld3(S.xprop + X_GRAV), d0, d1);
-            S2_congruence(ld3(S.x + X_GRAV), ld3(S.xprop + X_GRAV), d0, d1, S.M2);
+            S2_boxminus_B(ld3(S.x + X_GRAV), ld3(S.xprop + X_GRAV), S.Bprop, d0, d1);
+            S2_congruence_B(ld3(S.x + X_GRAV), ld3(S.xprop + X_GRAV), S.Bprop, d0, d1, S.M2);
             S.dx[21] = d0; S.dx[22] = d1;
             S.dxn[21] = S.M2[0] * d0 + S.M2[1] * d1;
             S.dxn[22] = S.M2[2] * d0 + S.M2[3] * d1;
@@ -244,10 +253,17 @@ __device__ void sol_prepare(SolverSm& S) {
 __device__ void sol_reduce(SolverSm& S, const double* __restrict__ partials, int nwork) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll 4
-    for (int b = warp; b < nwork; b += UPD_WARPS) {
-        const double* row = partials + (size_t)b * PSTRIDE;
-        a0 += __ldcg(&row[lane]); a1 += __ldcg(&row[lane + 32]); a2 += __ldcg(&row[lane + 64]);
+    for (int b = warp; b < nwork; b += 8 * UPD_WARPS) {          // eight rows per step: 24 loads in flight, then summed in row order
+        double v[8][3];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int bb = b + k * UPD_WARPS;
+            const double* row = partials + (size_t)bb * PSTRIDE;
+            v[k][0] = v[k][1] = v[k][2] = 0.0;
+            if (bb < nwork) { v[k][0] = __ldcg(&row[lane]); v[k][1] = __ldcg(&row[lane + 32]); v[k][2] = __ldcg(&row[lane + 64]); }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { a0 += v[k][0]; a1 += v[k][1]; a2 += v[k][2]; }
     }
     S.wred[warp][lane] = a0; S.wred[warp][lane + 32] = a1; S.wred[warp][lane + 64] = a2;
     __syncthreads();
@@ -454,7 +470,7 @@ __device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, unsigned lo
     if (warp == 2 && lane == 0) {
         const D3 g = S2_boxplus(ld3(S.x + X_GRAV), S.dxu[21], S.dxu[22]);                           // S2.hpp:136-142
         st3(S.xnew + X_GRAV, g);
-        if (finish) S2_congruence(g, ld3(S.xprop + X_GRAV), S.dxu[21], S.dxu[22], S.M2);
+        if (finish) S2_congruence_B(g, ld3(S.xprop + X_GRAV), S.Bprop, S.dxu[21], S.dxu[22], S.M2);
     }
     if (warp == 3 && lane < 9) {
         const int b = lane / 3, c = lane % 3;
@@ -466,6 +482,28 @@ __device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, unsigned lo
         if (tid >= 224 && tid < 236) lg->Hth[tid - 224] = S.red[78 + tid - 224];
         if (tid == 255) { lg->searched = S.searched; lg->effct = S.effct; lg->res_sum = S.red[91]; lg->valid = 1; lg->converged = S.converge; }
     }
+    if (finish && warp >= 4) {
+        // final covariance (:1834-1927):  P = T2 (Pt - (Pt[:, :ne] / R) W Pt[:ne, :]) T2^T.  The part that needs neither the new
+        // state nor the congruence at dx_ is formed by warps 4..7 while warps 1..3 are still busy with those.
+        const int t4 = tid - 128;
+#pragma unroll 1
+        for (int e = t4; e < NE * n; e += 128) {
+            const int a = e / n, j = e - a * n;
+            double v = 0.0;
+#pragma unroll
+            for (int b = 0; b < NE; b++) v = fma(S.Wm[a * 13 + 1 + b], S.Pt[b * n + j], v);
+            S.Y[e] = v;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+        for (int e = t4; e < n * n; e += 128) {
+            const int i = e / n, j = e - i * n;
+            double v = 0.0;
+#pragma unroll
+            for (int a = 0; a < NE; a++) v = fma(S.Pt[i * n + a] * Rinv, S.Y[a * n + j], v);
+            S.W1[e] = S.Pt[e] - v;
+        }
+    }
     __syncthreads();
     if (tid < XLEN) { ctl->x[tid] = S.xnew[tid]; if (lg) lg->x_after[tid] = S.xnew[tid]; }
     if (tid == 32) { ctl->t = S.t; ctl->converge = S.converge; ctl->iter = S.iter + 1; ctl->n_pass = S.n_pass + 1; ctl->done = finish; }
@@ -474,25 +512,6 @@ __device__ void sol_pass(SolverSm& S, FilterCtl* ctl, PassLog* logs, unsigned lo
 #pragma unroll 1
         for (int e = tid; e < n * n; e += UPD_THREADS) ctl->P[e] = S.Pt[e];
     } else {
-        // final covariance (:1834-1927):  P = T2 (Pt - (Pt[:, :ne] / R) W Pt[:ne, :]) T2^T
-#pragma unroll 1
-        for (int e = tid; e < NE * n; e += UPD_THREADS) {
-            const int a = e / n, j = e - a * n;
-            double v = 0.0;
-#pragma unroll
-            for (int b = 0; b < NE; b++) v = fma(S.Wm[a * 13 + 1 + b], S.Pt[b * n + j], v);
-            S.Y[e] = v;
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int e = tid; e < n * n; e += UPD_THREADS) {
-            const int i = e / n, j = e - i * n;
-            double v = 0.0;
-#pragma unroll
-            for (int a = 0; a < NE; a++) v = fma(S.Pt[i * n + a] * Rinv, S.Y[a * n + j], v);
-            S.W1[e] = S.Pt[e] - v;
-        }
-        __syncthreads();
 #pragma unroll 1
         for (int e = tid; e < n * n; e += UPD_THREADS) {            // rows
             const int i = e / n, j = e - i * n;

@@ -123,11 +123,13 @@ __device__ __forceinline__ void knn_leaf(const MapView& m, int leaf, float qx, f
             continue;
         }
 #pragma unroll 1
-        for (int it = 0; it < KNN_K; it++) {
+        while (true) {
             const unsigned best = __reduce_min_sync(FULL, key);
             if (best >= __float_as_uint(kb.w)) break;       // nothing strictly closer than the k-th best is left (covers the marker)
             const int src = __ffs(__ballot_sync(FULL, key == best)) - 1;
-            kb.insert(__uint_as_float(best), leaf * LEAF + src, lane);
+            const int cidx = leaf * LEAF + src;
+            // a walk seeded with candidates found elsewhere (knn_block) meets them again here: never list a slot twice
+            if (!__any_sync(FULL, lane < KNN_K && kb.idx == cidx)) kb.insert(__uint_as_float(best), cidx, lane);
             if (lane == src) key = INF_BITS;
         }
         leaf = nxt;
@@ -188,9 +190,9 @@ __device__ __forceinline__ void knn_root(const MapView& m, float qx, float qy, f
     }
 }
 
-// Exact k-nearest-neighbour search for one query by one warp.
-__device__ __forceinline__ void knn_query(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
-    kb.init();
+// Exact k-nearest-neighbour search for one query by one warp, continuing from the list in kb (empty after kb.init(), or seeded
+// with live points and their true distances).
+__device__ __forceinline__ void knn_query_from(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
     switch (m.n_levels) {
         case 1: knn_root<1>(m, qx, qy, qz, kb, lane); break;
         case 2: knn_root<2>(m, qx, qy, qz, kb, lane); break;
@@ -199,6 +201,11 @@ __device__ __forceinline__ void knn_query(const MapView& m, float qx, float qy, 
         case 5: knn_root<5>(m, qx, qy, qz, kb, lane); break;
         default: knn_root<6>(m, qx, qy, qz, kb, lane); break;
     }
+}
+
+__device__ __forceinline__ void knn_query(const MapView& m, float qx, float qy, float qz, KBest& kb, int lane) {
+    kb.init();
+    knn_query_from(m, qx, qy, qz, kb, lane);
 }
 
 // ----------------------------------------------------------------------------- box query
@@ -333,50 +340,46 @@ __device__ __forceinline__ int cell_list(const CellDir& D, unsigned long long ke
     return (start >= 0 && cnt <= room && cnt > 0) ? 1 : -1;
 }
 
+// one candidate (a deleted point keeps its listings: it is skipped by its flag)
+__device__ __forceinline__ void cell_consider(const float4& p, int idx, float qx, float qy, float qz, TBest& kb) {
+    if (slot_valid(p)) {
+        const float dd = sq_dist3(qx, qy, qz, p.x, p.y, p.z);
+        if (dd < kb.d[KNN_K - 1]) kb.insert(dd, idx);
+    }
+}
+
 // Score the halo list [start, start + cnt), eight candidates at a time: their point loads are issued together and the indices of
 // the next eight are fetched while these are scored (a scan is only a few warps per SM: the chain of dependent loads of one
 // thread IS the run time -- probe, first indices, then one round trip per eight candidates).
-// FILTER: accept only points whose cell coordinate on axis a equals want[a], for the axes with want[a] != INT_MIN (used by the
-// extension below, where a second list overlaps the first).
-template <bool FILTER>
-__device__ __forceinline__ void cell_scan_list(const MapView& m, int start, int cnt, float qx, float qy, float qz, TBest& kb,
-                                               int wantx, int wanty, int wantz) {
+__device__ __forceinline__ void cell_scan_list(const MapView& m, int start, int cnt, float qx, float qy, float qz, TBest& kb) {
     const int4* list = reinterpret_cast<const int4*>(m.dir.lists + start);
-    const float inv = m.dir.inv_cell;
     const int nchunks = (cnt + 7) >> 3;
     int4 ia = __ldg(&list[0]), ib = make_int4(0, 0, 0, 0);
     if (cnt > 4) ib = __ldg(&list[1]);
 #pragma unroll 1
     for (int c = 0; c < nchunks; c++) {
         const int n8 = cnt - 8 * c;                                            // candidates left, >= 1
-        float4 p[8];
-#pragma unroll
-        for (int k = 1; k < 8; k++) p[k] = make_float4(0.f, 0.f, 0.f, 0.f);   // flag 0: not a live point
-        p[0] = __ldg(&m.pts[ia.x]);
-        if (n8 > 1) p[1] = __ldg(&m.pts[ia.y]);
-        if (n8 > 2) p[2] = __ldg(&m.pts[ia.z]);
-        if (n8 > 3) p[3] = __ldg(&m.pts[ia.w]);
-        if (n8 > 4) p[4] = __ldg(&m.pts[ib.x]);
-        if (n8 > 5) p[5] = __ldg(&m.pts[ib.y]);
-        if (n8 > 6) p[6] = __ldg(&m.pts[ib.z]);
-        if (n8 > 7) p[7] = __ldg(&m.pts[ib.w]);
+        float4 p0, p1, p2, p3, p4, p5, p6, p7;
+        p1 = p2 = p3 = p4 = p5 = p6 = p7 = make_float4(0.f, 0.f, 0.f, 0.f);  // flag 0: not a live point
+        p0 = __ldg(&m.pts[ia.x]);
+        if (n8 > 1) p1 = __ldg(&m.pts[ia.y]);
+        if (n8 > 2) p2 = __ldg(&m.pts[ia.z]);
+        if (n8 > 3) p3 = __ldg(&m.pts[ia.w]);
+        if (n8 > 4) p4 = __ldg(&m.pts[ib.x]);
+        if (n8 > 5) p5 = __ldg(&m.pts[ib.y]);
+        if (n8 > 6) p6 = __ldg(&m.pts[ib.z]);
+        if (n8 > 7) p7 = __ldg(&m.pts[ib.w]);
         int4 na = ia, nb = ib;
         if (n8 > 8) na = __ldg(&list[2 * c + 2]);
         if (n8 > 12) nb = __ldg(&list[2 * c + 3]);
-        const int id[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            bool ok = slot_valid(p[k]);                                        // a deleted point keeps its listings: skipped by its flag
-            if (FILTER) {
-                if (wantx != INT_MIN) ok = ok && cell_coord(p[k].x, inv) == wantx;
-                if (wanty != INT_MIN) ok = ok && cell_coord(p[k].y, inv) == wanty;
-                if (wantz != INT_MIN) ok = ok && cell_coord(p[k].z, inv) == wantz;
-            }
-            if (ok) {
-                const float dd = sq_dist3(qx, qy, qz, p[k].x, p[k].y, p[k].z);
-                if (dd < kb.d[KNN_K - 1]) kb.insert(dd, id[k]);
-            }
-        }
+        cell_consider(p0, ia.x, qx, qy, qz, kb);
+        cell_consider(p1, ia.y, qx, qy, qz, kb);
+        cell_consider(p2, ia.z, qx, qy, qz, kb);
+        cell_consider(p3, ia.w, qx, qy, qz, kb);
+        cell_consider(p4, ib.x, qx, qy, qz, kb);
+        cell_consider(p5, ib.y, qx, qy, qz, kb);
+        cell_consider(p6, ib.z, qx, qy, qz, kb);
+        cell_consider(p7, ib.w, qx, qy, qz, kb);
         ia = na; ib = nb;
     }
 }
@@ -388,11 +391,11 @@ __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, f
     if (D.cap == 0u) return false;
     const float inv = D.inv_cell;
     const int ix = cell_coord(qx, inv), iy = cell_coord(qy, inv), iz = cell_coord(qz, inv);
-    if (abs(ix) >= CELL_CLAMP - 2 || abs(iy) >= CELL_CLAMP - 2 || abs(iz) >= CELL_CLAMP - 2) return false;
+    if (abs(ix) >= CELL_CLAMP - 1 || abs(iy) >= CELL_CLAMP - 1 || abs(iz) >= CELL_CLAMP - 1) return false;
     // ---- 1. + 2. the halo list of the query's cell: every point of the 3x3x3 block of cells around it
     int start, cnt;
     if (cell_list(D, cell_key(ix, iy, iz), start, cnt) <= 0) return false;
-    cell_scan_list<false>(m, start, cnt, qx, qy, qz, kb, INT_MIN, INT_MIN, INT_MIN);
+    cell_scan_list(m, start, cnt, qx, qy, qz, kb);
     if (kb.idx[KNN_K - 1] < 0) return false;
     // ---- 3. proof: every point outside the block is at least g away.  The distances from the query to the faces of its own cell
     // are shrunk by more than any rounding of the cell arithmetic.
@@ -402,30 +405,7 @@ __device__ __forceinline__ bool cell_knn(const MapView& m, float qx, float qy, f
     const float loy = fmaxf(qy - (float)iy * c - marg, 0.f), hiy = fmaxf((float)(iy + 1) * c - qy - marg, 0.f);
     const float loz = fmaxf(qz - (float)iz * c - marg, 0.f), hiz = fmaxf((float)(iz + 1) * c - qz - marg, 0.f);
     const float c1 = c - marg;
-    float gx = fminf(lox, hix) + c1, gy = fminf(loy, hiy) + c1, gz = fminf(loz, hiz) + c1;      // distance to the block's nearest face, per axis
-    if (kb.d[KNN_K - 1] < fminf(fminf(gx, gy), gz) * fminf(fminf(gx, gy), gz)) return true;
-    // ---- 4. extension.  The block's nearest face is too close on some axes: on each of them grow the block by one slab of cells
-    // on that side.  The slab(s) are covered by the halo lists of the cells at offset e = (ex, ey, ez) (e_a = the side on a grown
-    // axis, 0 elsewhere) and of every combination with some components zeroed; a point is taken from the ONE list whose non-zero
-    // components are exactly the axes on which the point lies in the new slab, so nothing is scored twice.
-    const float w = kb.d[KNN_K - 1];
-    const int ex = gx * gx <= w ? (lox < hix ? -1 : 1) : 0;
-    const int ey = gy * gy <= w ? (loy < hiy ? -1 : 1) : 0;
-    const int ez = gz * gz <= w ? (loz < hiz ? -1 : 1) : 0;
-#pragma unroll 1
-    for (int combo = 1; combo < 8; combo++) {
-        const int dx = (combo & 1) ? ex : 0, dy = (combo & 2) ? ey : 0, dz = (combo & 4) ? ez : 0;
-        if (((combo & 1) && !ex) || ((combo & 2) && !ey) || ((combo & 4) && !ez)) continue;       // that axis is not grown
-        int st2, cn2;
-        const int have = cell_list(D, cell_key(ix + dx, iy + dy, iz + dz), st2, cn2);
-        if (have < 0) return false;
-        if (have == 0) continue;                // nothing within a cell's width of that cell: nothing to add
-        cell_scan_list<true>(m, st2, cn2, qx, qy, qz, kb, dx ? ix + 2 * dx : INT_MIN, dy ? iy + 2 * dy : INT_MIN, dz ? iz + 2 * dz : INT_MIN);
-    }
-    // the grown block: on a grown axis the far face of the new slab or the untouched opposite face, whichever is nearer
-    if (ex) gx = fminf(fminf(lox, hix) + c + c1, fmaxf(lox, hix) + c1);
-    if (ey) gy = fminf(fminf(loy, hiy) + c + c1, fmaxf(loy, hiy) + c1);
-    if (ez) gz = fminf(fminf(loz, hiz) + c + c1, fmaxf(loz, hiz) + c1);
+    const float gx = fminf(lox, hix) + c1, gy = fminf(loy, hiy) + c1, gz = fminf(loz, hiz) + c1;      // distance to the block's nearest face, per axis
     const float g = fminf(fminf(gx, gy), gz);
     return kb.d[KNN_K - 1] < g * g;
 }
@@ -441,7 +421,7 @@ struct WalkPool {
     int n[2];                      // the counter of the current call and, being cleared, that of the next (see knn_block)
     int who[WALK_POOL];
     float x[WALK_POOL], y[WALK_POOL], z[WALK_POOL];
-    float rd[WALK_POOL][KNN_K];
+    float rd[WALK_POOL][KNN_K];    // in: the k candidates the thread search found (a bound for the walk; +inf / -1 when it found fewer); out: the answer
     int ri[WALK_POOL][KNN_K];
 };
 __device__ __forceinline__ void knn_block(const MapView& m, bool active, float qx, float qy, float qz, TBest& kb, WalkPool& W, int& phase) {
@@ -453,15 +433,27 @@ __device__ __forceinline__ void knn_block(const MapView& m, bool active, float q
     int* counter = &W.n[phase & 1];
     if (active && !exact) {
         mine = atomicAdd(counter, 1);
-        if (mine < WALK_POOL) { W.who[mine] = (int)threadIdx.x; W.x[mine] = qx; W.y[mine] = qy; W.z[mine] = qz; }
+        if (mine < WALK_POOL) {
+            W.who[mine] = (int)threadIdx.x; W.x[mine] = qx; W.y[mine] = qy; W.z[mine] = qz;
+            const bool full = kb.idx[KNN_K - 1] >= 0;         // seed only with a complete list (its k-th distance bounds the walk)
+#pragma unroll
+            for (int j = 0; j < KNN_K; j++) { W.rd[mine][j] = full ? kb.d[j] : INFINITY; W.ri[mine][j] = full ? kb.idx[j] : -1; }
+        }
     }
     __syncthreads();
     const int total = *counter, n = min(total, WALK_POOL);
     if (threadIdx.x == 0) W.n[(phase + 1) & 1] = 0;     // nobody touches the other counter before the next call's first barrier
     phase++;
     for (int i = warp; i < n; i += nwarps) {
+        // the walk starts from what the thread search found: with the k-th distance as its bound it only enters boxes that cut
+        // the known ball (a handful of dependent loads instead of a full descent)
         KBest w;
-        knn_query(m, W.x[i], W.y[i], W.z[i], w, lane);
+        w.init();
+        if (lane < KNN_K) { w.d = W.rd[i][lane]; w.idx = W.ri[i][lane]; }
+        w.w = __shfl_sync(FULL, w.d, KNN_K - 1);
+        w.n = w.w < INFINITY ? KNN_K : 0;
+        knn_query_from(m, W.x[i], W.y[i], W.z[i], w, lane);
+        __syncwarp();
         if (lane < KNN_K) { W.rd[i][lane] = w.d; W.ri[i][lane] = w.idx; }
     }
     // more unproven queries than the pool holds (a scan far from the map): their own warp walks them

@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) k_search(MapView m, Scan
     pdl_wait();                 // the previous pass's Kalman step (or the upload) is complete and visible
     pdl_launch();               // k_residual may start: its solver block prepares while we search
     if (ctl->done || !ctl->converge) return;
+    if (blockIdx.x == 0 && threadIdx.x < XLEN) const_cast<FilterCtl*>(ctl)->x_search[threadIdx.x] = ctl->x[threadIdx.x];
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * SEARCH_THREADS + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * SEARCH_THREADS) >> 5;
@@ -804,6 +805,7 @@ __global__ void __maxnreg__(96) k_search_c(MapView m, ScanView sc, const FilterC
     pdl_wait();
     pdl_launch();
     if (ctl->done || !ctl->converge) return;
+    if (blockIdx.x == 0 && threadIdx.x < XLEN) const_cast<FilterCtl*>(ctl)->x_search[threadIdx.x] = ctl->x[threadIdx.x];
     if (threadIdx.x == 0) pool.n[0] = pool.n[1] = 0;
     __syncthreads();
     int phase = 0;
@@ -1150,7 +1152,7 @@ int Filter::init() {
 int Filter::reserve(int nq) {
     FL_CHECK(body_.reserve(sizeof(float4) * (size_t)nq));
     FL_CHECK(nearest_.reserve(sizeof(float4) * KNN_K * (size_t)nq));
-    FL_CHECK(nearest_cnt_.reserve(sizeof(int) * (size_t)nq));
+    { const size_t had = nearest_cnt_.bytes; FL_CHECK(nearest_cnt_.reserve(sizeof(int) * (size_t)nq)); if (nearest_cnt_.bytes != had) FL_CUDA(cudaMemsetAsync(nearest_cnt_.ptr, 0, nearest_cnt_.bytes, stream())); }
     FL_CHECK(selected_.reserve((size_t)nq));
     FL_CHECK(normvec_.reserve(sizeof(float4) * (size_t)nq));
     scan_.nearest = nearest_.as<float4>();
@@ -1228,9 +1230,51 @@ int Filter::restore_state() {
     return FL_OK;
 }
 
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Nearest_Points of the points other ranks own: the same search, with the state the last searching pass used, on this rank's
+// (identical) map replica -- bit-identical to what the owning rank cached.
+int Filter::complete_neighbours() {
+    if (neighbours_complete_ || (scan_.q_begin <= 0 && scan_.q_end >= scan_.Q)) { neighbours_complete_ = true; return FL_OK; }
+    FL_CUDA(cudaSetDevice(map_->device()));
+    const int keep_b = scan_.q_begin, keep_e = scan_.q_end;
+    const int ranges[2][2] = {{0, keep_b}, {keep_e, scan_.Q}};
+    for (int r = 0; r < 2; r++) {
+        if (ranges[r][1] <= ranges[r][0]) continue;
+        scan_.q_begin = ranges[r][0]; scan_.q_end = ranges[r][1];
+        UpdArgs a;
+        a.m = map_->view();
+        if (search_mode_ == 0) a.m.dir.cap = 0;
+        a.sc = scan_; a.ctl = ctl_.as<FilterCtl>(); a.partials = partials_.as<double>(); a.red_g = red_.as<double>();
+        a.logs = logs_.as<PassLog>(); a.p2p = p2p_.as<P2PState>();
+        a.mode = 0; a.max_passes = 1; a.search_only = 1; a.dbg = 0; a.pose_from_search = 1;
+        a.pub = pub_.as<unsigned long long>(); a.nonce = ++launch_nonce_;
+        const int cap = upd_capacity_[extrinsic_est_ ? 1 : 0];
+        const int nq = scan_.q_end - scan_.q_begin;
+        const int workers = std::max(1, std::min(cap - 1, (nq + UPD_THREADS - 1) / UPD_THREADS));
+        cudaError_t e = extrinsic_est_ ? launch_pdl(k_update<true>, workers + 1, UPD_THREADS, stream(), false, a)
+                                       : launch_pdl(k_update<false>, workers + 1, UPD_THREADS, stream(), false, a);
+        if (e != cudaSuccess) { scan_.q_begin = keep_b; scan_.q_end = keep_e; set_last_error("complete_neighbours: %s", cudaGetErrorString(e)); return FL_ERR_CUDA; }
+    }
+    scan_.q_begin = keep_b; scan_.q_end = keep_e;
+    neighbours_complete_ = true;
+    return FL_OK;
+}
+
 int Filter::run_passes() {
     FL_CUDA(cudaSetDevice(map_->device()));
     if (scan_.q_end > scan_.Q) { set_last_error("shard exceeds the scan"); return FL_ERR_ARG; }
+    neighbours_complete_ = false;
     launches_ = 0;
     if (fused()) {
         cudaStream_t st = stream();
@@ -1268,18 +1312,6 @@ int Filter::run_passes() {
     return FL_OK;
 }
 
-template <class... KArgs, class... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
 // the fused persistent kernel: blockIdx 0 solves, the others measure; every block must be co-resident (they wait for each other)
 int Filter::launch_update(int max_passes, int mode, int search_only) {
     FL_CUDA(cudaSetDevice(map_->device()));
@@ -1292,6 +1324,7 @@ int Filter::launch_update(int max_passes, int mode, int search_only) {
     a.mode = mode; a.max_passes = max_passes; a.search_only = search_only;
     a.pub = pub_.as<unsigned long long>(); a.nonce = ++launch_nonce_;
     { const char* e = getenv("FASTLIO_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
+    a.pose_from_search = 0;
     const int cap = upd_capacity_[extrinsic_est_ ? 1 : 0];
     // every co-resident block works (a searching pass wants many warps in flight); small scans: at least 4 points per warp
     // one thread per point: full warps (the search is bound by a thread's own chain of loads, not by the number of SMs)
@@ -1406,6 +1439,7 @@ int Filter::map_incremental(double fsm, int ekf_inited, int* n_to_add, int* n_no
     if (nq <= 0) return FL_OK;
     if (!(fsm > 0.0)) { set_last_error("map_incremental: filter_size_map_min must be > 0"); return FL_ERR_ARG; }
     FL_CUDA(cudaSetDevice(map_->device()));
+    FL_CHECK(complete_neighbours());          // sharded update: every rank must classify the WHOLE scan the same way
     cudaStream_t st = stream();
     FL_CHECK(mi_world_.reserve(sizeof(float4) * (size_t)nq));
     FL_CHECK(mi_flag_add_.reserve((size_t)nq));
@@ -1442,6 +1476,7 @@ int Filter::map_incremental(double fsm, int ekf_inited, int* n_to_add, int* n_no
 int Filter::get_nearest(float* out_pts, int* out_cnt, int nq) {
     if (nq > scan_.Q) { set_last_error("get_nearest: nq exceeds the bound scan"); return FL_ERR_ARG; }
     FL_CUDA(cudaSetDevice(map_->device()));
+    FL_CHECK(complete_neighbours());
     if (out_pts) FL_CUDA(cudaMemcpyAsync(out_pts, scan_.nearest, sizeof(float4) * KNN_K * (size_t)nq, cudaMemcpyDeviceToHost, stream()));
     if (out_cnt) FL_CUDA(cudaMemcpyAsync(out_cnt, scan_.nearest_cnt, sizeof(int) * (size_t)nq, cudaMemcpyDeviceToHost, stream()));
     FL_CUDA(cudaStreamSynchronize(stream()));
@@ -1449,6 +1484,10 @@ int Filter::get_nearest(float* out_pts, int* out_cnt, int nq) {
 }
 int Filter::get_selected(unsigned char* out, int nq) {
     if (nq > scan_.Q) { set_last_error("get_selected: nq exceeds the bound scan"); return FL_ERR_ARG; }
+    if (scan_.q_begin > 0 || scan_.q_end < nq) {
+        set_last_error("get_selected: point_selected_surf of points outside this rank's shard [%d, %d) lives on the rank that owns them", scan_.q_begin, scan_.q_end);
+        return FL_ERR_STATE;
+    }
     FL_CUDA(cudaSetDevice(map_->device()));
     FL_CUDA(cudaMemcpyAsync(out, scan_.selected, (size_t)nq, cudaMemcpyDeviceToHost, stream()));
     FL_CUDA(cudaStreamSynchronize(stream()));

@@ -37,6 +37,7 @@ struct FilterCtl {
     double P[NDOF * NDOF];
     double P_prop[NDOF * NDOF];
     long long prof[16];  // clock64() stamps of the last solve_pass (thread 0), for tuning
+    double x_search[XLEN];   // the state the last searching pass used (Nearest_Points belong to it)
     FilterCtl* host_mirror;  // page-locked, device-mapped copy on the host: the pass that ends the update stores the result there
 };
 
@@ -95,6 +96,9 @@ public:
     // state and its cached neighbours, then Add_Points(PointToAdd, true) + Add_Points(PointNoNeedDownsample, false)
     int map_incremental(double filter_size_map_min, int ekf_inited, int* n_to_add, int* n_no_downsample, int* added);
     int get_nearest(float* out_pts, int* out_cnt, int nq);
+    // multi-GPU: Nearest_Points of the points outside this rank's shard (searched by their own rank during the update) are
+    // recomputed here, with the state of the last searching pass, before anything reads the whole scan's neighbours
+    int complete_neighbours();
     int get_selected(unsigned char* out, int nq);
     int get_pass_logs(PassLog* out, int cap, int* n);
     // multi-GPU: scan points sharded across ranks, map replicated, one all-reduce per pass
@@ -145,6 +149,7 @@ private:
     int launches_ = 0;
     long long host_ns_[4] = {0, 0, 0, 0};
     bool shard_set_ = false;
+    bool neighbours_complete_ = true;
     // NCCL (resolved lazily with dlopen so that single-GPU use needs no NCCL at all)
     NcclApi* nccl_ = nullptr;
     void* comm_ = nullptr;

@@ -46,6 +46,7 @@ struct UpdArgs {
     int max_passes;        // passes this launch may run (persistent: max_iter + 1; NCCL chain: 1)
     int search_only;       // 1: the kNN phase of one searching pass alone (neighbours + gate), for timing
     int dbg;               // tuning switches (FASTLIO_B200_DBG)
+    int pose_from_search;  // search_only: transform with ctl->x_search (the state of the last searching pass) instead of ctl->x
 };
 
 struct SolverSm {
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
                 // the state this launch starts from is in the control block (uploaded / left by the previous launch)
                 if (__ldcg(&ctl->done)) return;
                 searched = __ldcg(&ctl->converge) != 0 || a.search_only;      // dyn_share.converge (laserMapping.cpp:667)
-                s = load_pose(ctl->x);
+                s = load_pose(a.pose_from_search ? ctl->x_search : ctl->x);
             } else {
                 // later passes: wait for the solver block's publication of pass p (tagged words, see pub_publish)
                 const unsigned tag = pub_tag(a.nonce, p);
@@ -634,6 +635,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
     int p = 0;
     for (; p < a.max_passes && !S.done; p++) {
         if (tid == 0) ctl->prof[0] = clock64();
+        if (S.converge && tid < XLEN) ctl->x_search[tid] = S.x[tid];      // this pass searches: Nearest_Points will belong to this state
         if (a.mode != 1) sol_prepare(S);                 // overlaps the workers' measurement
         if (tid == 0) ctl->prof[8] = clock64();
         if (a.mode != 3) {

@@ -32,4 +32,13 @@ xs = torch.tensor(x, device="cuda"); ref = xs.clone(); dist.broadcast(ref, src=0
 same = bool((xs == ref).all().item())
 print(f"[{comm}] rank {rank}/{world}: shard [{lo},{hi}) |x - x_1gpu|={dx:.3e} |P - P_1gpu|={dP:.3e} identical_to_rank0={same} passes={len(f.pass_logs())}", flush=True)
 assert dx < 1e-9 and dP < 1e-9 and same
+# the replicated map mutation: every rank classifies the whole scan (the neighbours of the other ranks' shards are recomputed
+# locally) and applies the same Add_Points -- the replicas must stay identical
+res = f.map_incremental(0.5, True)
+fl = t.flatten()
+order = np.lexsort((fl[:, 3], fl[:, 2], fl[:, 1], fl[:, 0]))
+digest = torch.tensor([float(t.validnum()), float(np.float64(fl[order, :3].astype(np.float64).sum())), float(res[0]), float(res[1]), float(res[2])], device="cuda", dtype=torch.float64)
+ref = digest.clone(); dist.broadcast(ref, src=0)
+print(f"[{comm}] rank {rank}: map_incremental {res}, map now {t.validnum()} points, replica identical to rank 0: {bool((digest == ref).all().item())}", flush=True)
+assert bool((digest == ref).all().item())
 dist.barrier(); dist.destroy_process_group()

@@ -117,6 +117,36 @@ def test_shard_equals_subscan(problems):
     assert np.allclose(total, full.pass_logs()[0]["HtH"], rtol=1e-12, atol=1e-9)
 
 
+def test_sharded_update_completes_the_neighbours_of_the_whole_scan(problems):
+    """Multi-GPU building block on one GPU: a rank searches only its shard during the update, but map_incremental
+    and get_nearest need Nearest_Points of the WHOLE scan, from the state of the last searching pass -- the rank recomputes the
+    others' on its own map replica.  They must be exactly what an unsharded search at that state returns."""
+    pr = problems("small")
+    n = len(pr.scan)
+    t = api.KdTree(0, 0.5); t.Build(pr.map_pts)
+    lo, hi = api.shard_range(n, 3, 1)
+    f = api.Esekf(t, max_points=n, max_iter=pr.cfg.max_iter)
+    f.upload_scan(pr.scan); f.set_shard(lo, hi); f.upload_state(pr.x_prior, pr.P_prior, pr.R); f.run()
+    x, P, npass = f.download_state()
+    logs = f.pass_logs()
+    last_search = max(i for i, l in enumerate(logs) if l["searched"])
+    x_search = pr.x_prior if last_search == 0 else logs[last_search - 1]["x_after"]
+    near, cnt = f.nearest(n)
+    q = np.zeros((n, 4), dtype=np.float32)
+    tmp = np.zeros(3, dtype=np.float32)
+    for i in range(n):
+        bind.lib().oracle_transform_point(np.ascontiguousarray(x_search), np.ascontiguousarray(pr.scan[i, :3]), tmp)
+        q[i, :3] = tmp
+    gp, gd, gc = t.Nearest_Search(q, 5)
+    assert np.array_equal(cnt, gc)
+    assert np.array_equal(near, gp)
+    with pytest.raises(api.FastLioError):
+        f.selected(n)                              # point_selected_surf of the other shards lives on their ranks
+    # and the device-side map_incremental classifies the whole scan
+    to_add, no_ds, added = f.map_incremental(0.5, True)
+    assert to_add + no_ds > 0
+
+
 def test_small_m_branch(problems):
     """Fewer than 23 effective points -> the K = P H^T (H P H^T / R + I)^-1 / R branch (esekfom.hpp:1715-1744)."""
     pr = problems("tiny")

@@ -350,7 +350,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 geometry / f64 filter", "data": "synthetic",
             "config": {"workload": args.workload, "n_map": pr.cfg.n_map, "n_scan": pr.cfg.n_scan,
                        "max_iteration": pr.cfg.max_iter, "passes_per_scan": n_pass, "solver": args.solver,
-                       "parallelism": (f"scan-shard x{world}, map replicated, 92 f64 summed per pass via " + ("peer-memory mailboxes fused in k_residual" if args.comm == "p2p" else "ncclAllReduce")) if world > 1 else "1 GPU",
+                       "parallelism": (f"scan-shard x{world}, map replicated, 92 f64 summed per pass via " + ("peer-memory mailboxes inside the persistent k_update kernel (solver block)" if args.comm == "p2p" else "ncclAllReduce")) if world > 1 else "1 GPU",
                        "l2": "flushed (256 MB memset) before every timed step; map (~21 MB) would otherwise be L2-resident"},
             "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(pr.scan.nbytes + (26 + 529 + 32) * 8),
                     "d2h_bytes_per_step": int((26 + 529 + 32) * 8), "ms_per_step": 1e3 * e2e_s / args.steps,

@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
             bool searched;
             if (p == 0) {
                 // the state this launch starts from is in the control block (uploaded / left by the previous launch)
-                if (__ldcg(&ctl->done)) return;
+                if (__ldcg(&ctl->done) && !a.search_only) return;      // (a search-only launch may follow a finished update)
                 searched = __ldcg(&ctl->converge) != 0 || a.search_only;      // dyn_share.converge (laserMapping.cpp:667)
                 s = load_pose(a.pose_from_search ? ctl->x_search : ctl->x);
             } else {

@@ -812,6 +812,8 @@ int Map::build_directory() {
         FL_CHECK(dir_lists_.reserve(sizeof(int) * pool));
         v_.dir.lists = dir_lists_.as<int>();
         v_.dir.lists_cap = (int)std::min<size_t>(dir_lists_.bytes / sizeof(int), 0x7ffffff0ull);
+        // the slack at the end of a list is read (and ignored) by the 16-byte loads of the search: keep it defined
+        FL_CUDA(cudaMemsetAsync(dir_lists_.ptr, 0, sizeof(int) * (size_t)v_.dir.lists_cap, stream_));
         k_halo_alloc<<<blocks_for(v_.dir.cap, 256), 256, 0, stream_>>>(v_, d_cnt);
         k_halo_fill<<<nb, 256, 0, stream_>>>(v_, used);
         FL_CUDA(cudaGetLastError());

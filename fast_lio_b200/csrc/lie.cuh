@@ -161,12 +161,16 @@ FL_HD M33 A_matrix(const D3& v) {
 
 // ---- S2, S2_typ == 1 (S2.hpp:214-239)
 FL_HD void S2_Bx(const D3& v, double B[6]) {          // 3x2 row-major
+    // S2.hpp:214-239 divides every entry by (L + v.x) and by L; here ONE reciprocal each (this runs in the single-warp solver,
+    // where an FP64 division is ~40 dependent instructions) -- the entries differ from the reference's by at most an ulp
     const double L = S2_LEN;
+    constexpr double invL = 1.0 / S2_LEN;
     if (v.x + L > MTK_TOL) {
-        B[0] = -v.y;                     B[1] = -v.z;
-        B[2] = L - v.y * v.y / (L + v.x); B[3] = -v.z * v.y / (L + v.x);
-        B[4] = -v.z * v.y / (L + v.x);    B[5] = L - v.z * v.z / (L + v.x);
-        for (int i = 0; i < 6; i++) B[i] /= L;
+        const double r = 1.0 / (L + v.x);
+        const double yy = v.y * v.y * r, zy = v.z * v.y * r, zz = v.z * v.z * r;
+        B[0] = -v.y * invL;      B[1] = -v.z * invL;
+        B[2] = (L - yy) * invL;  B[3] = -zy * invL;
+        B[4] = -zy * invL;       B[5] = (L - zz) * invL;
     } else {
         for (int i = 0; i < 6; i++) B[i] = 0;
         B[3] = -1; B[4] = 1;

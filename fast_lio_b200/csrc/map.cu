@@ -1020,7 +1020,7 @@ int Map::insert_device(const float4* d_pts, int n) {
     n_valid_ += n;
     // directory: out of room, or too many over-full cells (their queries walk the BVH) -> re-list the live slots
     if (v_.dir.cap) {
-        const bool crowded = h_counters_[C_DIR_CROWDED] > std::max(64, h_counters_[C_DIR_CELLS] / 128);
+        const bool crowded = h_counters_[C_DIR_CROWDED] > std::max(64, h_counters_[C_DIR_CELLS] / 1024);
         if (h_counters_[C_DIR_ERROR]) {
             dir_min_cap_ = std::max(dir_min_cap_, (size_t)v_.dir.cap + (size_t)v_.dir.cap / 2);
             dir_min_pool_ = std::max<size_t>(dir_min_pool_ * 2, (size_t)HALO_NEW_CAP * 262144);

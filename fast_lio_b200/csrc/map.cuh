@@ -38,7 +38,7 @@ namespace fl {
 constexpr int CELL_OFF = 1 << 20;                  // 21 bits per axis
 constexpr int CELL_CLAMP = (1 << 20) - 4;
 constexpr int HALO_MAX = 2048;                     // a cell whose block holds more points than this sends its queries to the BVH walk
-constexpr int HALO_NEW_CAP = 48;                   // room of a list created by an insert (lists made by a re-list get count + 25 %)
+constexpr int HALO_NEW_CAP = 64;                   // room of a list created by an insert (lists made by a re-list get count + 25 %)
 
 struct __align__(16) CellEntry {
     unsigned long long key;      // 0 = free, else cell_key()

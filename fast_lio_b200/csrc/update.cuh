@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(UpdArgs a) {
                 __stcg(&a.partials[(size_t)wb * PSTRIDE + tid], v);
             }
             __syncthreads();                                // the block's partial is written ...
-            if (tid == 0) { __threadfence(); atomicAdd(&ctl->ticket, 1); }      // ... and ordered before the ticket by ONE fence
+            if (tid == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(&ctl->ticket) : "memory");      // ... and ordered before the ticket (release)
             if (a.mode == 1) return;
         }
         return;

@@ -23,11 +23,14 @@ if world > 1:
     f.p2p_connect(world, rank, b"".join(handles))
     f.set_shard(*api.shard_range(n, world, rank))
 x, P, st = f.update_iterated_dyn_share_modified(pr.scan, pr.x_prior, pr.P_prior, pr.R)
+logs = f.pass_logs()
+if world == 1:
+    near, cnt = f.nearest(n)
+    sel = f.selected(n)
 f.upload_scan(pr.scan); f.upload_state(pr.x_prior, pr.P_prior, pr.R)
 f.time_resident(5, True)
 ms = f.time_resident(50, True) / 50
 ms_search = f.time_search_pass(20, True) / 20
-logs = f.pass_logs()
 out = {"workload": name, "n_gpus": world, "n_map": len(pr.map_pts), "n_scan": n, "build_s (host->device, k-d partition, directory)": round(t_build, 3),
        "ms_per_scan": ms, "scans_per_s": 1e3 / ms, "search_phase_ms": ms_search, "passes": len(logs), "effct": [l["effct"] for l in logs],
        "map": t.stats(), "directory": t.dir_stats()}
@@ -41,9 +44,8 @@ if rank == 0 and (len(sys.argv) < 3 or sys.argv[2] != "noref"):
                      "other_err": float(np.abs(x[7:] - o.x[7:]).max()),
                      "passes_equal": [(l["searched"], l["effct"], l["converged"]) for l in logs] == [(p["searched"], p["effct"], p["converged"]) for p in o.passes]}
     if world == 1:
-        near, cnt = f.nearest(n)
         out["parity"]["nearest_equal"] = bool(np.array_equal(near, o.nearest) and np.array_equal(cnt, o.nearest_cnt))
-        out["parity"]["selected_equal"] = bool(np.array_equal(f.selected(n), o.selected))
+        out["parity"]["selected_equal"] = bool(np.array_equal(sel, o.selected))
     out["parity"]["ok"] = bool(out["parity"]["pos_err"] <= 1e-4 and out["parity"]["rot_err"] <= 1e-4 and out["parity"]["passes_equal"])
 if rank == 0:
     print(json.dumps(out), flush=True)

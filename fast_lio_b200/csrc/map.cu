@@ -39,7 +39,7 @@ void DeviceBuffer::release() {
 
 // counters_ layout
 enum Counter { C_LEAF_USED = 0, C_DELETED, C_ADDED, C_GROUPS, C_NINSERT, C_TOMB, C_ERROR, C_COMPACT,
-               C_DIR_CELLS, C_DIR_POOL, C_DIR_CROWDED, C_DIR_ERROR, C_DIR_WALKED, C_REMOVED, C_REVIVED, C_NSLOTS, C_COUNT = 16 };
+               C_DIR_CELLS, C_DIR_POOL, C_DIR_CROWDED, C_DIR_ERROR, C_DIR_WALKED, C_REMOVED, C_REVIVED, C_NFIX, C_COUNT = 16 };
 
 // ============================================================================= kernels
 // ----------------------------------------------------------------------------- k-d partition build
@@ -299,8 +299,7 @@ __global__ void k_halo_fill(MapView m, int n_leaf_used) {
     }
 }
 // incremental, two kernels (claim, then append) so that nobody waits for a list that is still being set up.
-// One warp per inserted point, lane t < 27 its t-th cell.  slots[i] < 0: the point re-used the slot of a deleted point of its own
-// cell -- all 27 listings are already in place.
+// One warp per inserted point, lane t < 27 its t-th cell.  slots[i] < 0: the point could not be placed.
 __global__ void __launch_bounds__(256) k_halo_claim(MapView m, const float4* __restrict__ pts, const int* __restrict__ slots, int n, int* counters) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -316,7 +315,8 @@ __global__ void __launch_bounds__(256) k_halo_claim(MapView m, const float4* __r
         E.cnt_cap = (unsigned)HALO_NEW_CAP << 16;
     }
 }
-__global__ void __launch_bounds__(256) k_halo_append(MapView m, const float4* __restrict__ pts, const int* __restrict__ slots, int n, int* counters) {
+__global__ void __launch_bounds__(256) k_halo_append(MapView m, const float4* __restrict__ pts, const int* __restrict__ slots, int n, int* counters,
+                                                      unsigned* __restrict__ fix, int fix_cap) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
@@ -329,10 +329,61 @@ __global__ void __launch_bounds__(256) k_halo_append(MapView m, const float4* __
         const unsigned old = atomicAdd(&E.cnt_cap, 1u);
         const int pos = (int)(old & 0xffffu), room = (int)(old >> 16);
         if (pos < room) m.dir.lists[E.start + pos] = slot;
-        else {                                                       // no room: the cell is answered by the BVH walk until the next re-list
+        else {                                                       // no room: queue the cell for k_halo_fix (a new, larger list)
             atomicSub(&E.cnt_cap, 1u);
-            if (atomicExch(&E.start, -1) >= 0) atomicAdd(&counters[C_DIR_CROWDED], 1);
+            if (atomicExch(&E.start, -1) >= 0) {
+                const int at = atomicAdd(&counters[C_NFIX], 1);
+                if (at < fix_cap) fix[at] = e; else atomicAdd(&counters[C_DIR_CROWDED], 1);
+            }
         }
+    }
+}
+
+// Lists that ran out of room are made anew, larger, by one warp each: the live points of the cell's 3x3x3 block are found through
+// the BVH (box query over the block, exact membership by cell coordinate), counted, then listed.  The old list is abandoned in the
+// pool (the next global re-list packs it away).  A cell whose block holds more than HALO_MAX points stays with the BVH walk.
+struct HaloGather {
+    const MapView& m; int lane; int cx, cy, cz; int* out; int cnt = 0;
+    __device__ HaloGather(const MapView& m_, int lane_, int cx_, int cy_, int cz_, int* out_) : m(m_), lane(lane_), cx(cx_), cy(cy_), cz(cz_), out(out_) {}
+    __device__ __forceinline__ void leaf(int l) {
+        const float inv = m.dir.inv_cell;
+        while (l >= 0) {
+            const int slot = l * LEAF + lane;
+            const float4 p = m.pts[slot];
+            const bool in = slot_valid(p) && abs(cell_coord(p.x, inv) - cx) <= 1 && abs(cell_coord(p.y, inv) - cy) <= 1 && abs(cell_coord(p.z, inv) - cz) <= 1;
+            const unsigned mask = __ballot_sync(FULL, in);
+            if (out && in) { const int at = cnt + __popc(mask & ((1u << lane) - 1)); out[at] = slot; }
+            cnt += __popc(mask);
+            l = m.next[l];
+        }
+    }
+};
+__global__ void __launch_bounds__(256) k_halo_fix(MapView m, const unsigned* __restrict__ fix, int fix_cap, int* counters) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int n = min(counters[C_NFIX], fix_cap);
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        CellEntry& E = m.dir.tab[fix[i]];
+        const unsigned long long key = E.key;
+        const int cx = (int)((key >> 42) & 0x1fffffu) - CELL_OFF, cy = (int)((key >> 21) & 0x1fffffu) - CELL_OFF, cz = (int)(key & 0x1fffffu) - CELL_OFF;
+        const float c = m.dir.cell, pad = 1e-3f * c;
+        const float bmin[3] = {(cx - 1) * c - pad, (cy - 1) * c - pad, (cz - 1) * c - pad};
+        const float bmax[3] = {(cx + 2) * c + pad, (cy + 2) * c + pad, (cz + 2) * c + pad};
+        HaloGather count(m, lane, cx, cy, cz, nullptr);
+        box_query(m, bmin, bmax, count, lane);
+        const int cnt = count.cnt;
+        int start = -1, room = 0;
+        if (cnt <= HALO_MAX) {
+            room = (cnt + max(16, cnt / 2) + 3) & ~3;
+            if (lane == 0) start = atomicAdd(&counters[C_DIR_POOL], room);
+            start = __shfl_sync(FULL, start, 0);
+            if (start + room > m.dir.lists_cap) { start = -1; if (lane == 0) atomicExch(&counters[C_DIR_ERROR], 1); }
+        }
+        if (start < 0) { if (lane == 0) atomicAdd(&counters[C_DIR_CROWDED], 1); continue; }      // stays with the BVH walk
+        HaloGather fill(m, lane, cx, cy, cz, m.dir.lists + start);
+        box_query(m, bmin, bmax, fill, lane);
+        __syncwarp();
+        if (lane == 0) { E.cnt_cap = ((unsigned)room << 16) | (unsigned)fill.cnt; __threadfence(); E.start = start; }
     }
 }
 
@@ -597,9 +648,7 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
         while (!placed) {
             const float4 cur = m.pts[leaf * LEAF + lane];
             const int w = __float_as_int(cur.w);
-            // free: never used, or the slot of a deleted point of the SAME cell (its 27 directory listings then serve the new point)
-            const bool tomb_ok = (w == SLOT_TOMB || w == SLOT_TOMB_DS) && (m.dir.cap == 0u || same_cell(m.dir, cur, p));
-            unsigned freem = __ballot_sync(FULL, w == SLOT_FREE || tomb_ok);
+            unsigned freem = __ballot_sync(FULL, w == SLOT_FREE || w == SLOT_TOMB || w == SLOT_TOMB_DS);      // never used, or a deleted point's
             while (freem && !placed) {
                 const int s = __ffs(freem) - 1;
                 const int seen = __shfl_sync(FULL, w, s);
@@ -610,7 +659,7 @@ __global__ void __launch_bounds__(256) k_insert(MapView m, const float4* __restr
                     if (lane == 0) {
                         m.payload[leaf * LEAF + s] = p.w;
                         m.pts[leaf * LEAF + s] = make_float4(p.x, p.y, p.z, __int_as_float(SLOT_VALID));
-                        slot_out[i] = seen == SLOT_FREE ? leaf * LEAF + s : -1;
+                        slot_out[i] = leaf * LEAF + s;
                     }
                     placed = true;
                 } else {
@@ -656,7 +705,7 @@ Map::Map(int device, float downsample_size) : device_(device), downsample_(downs
 
 Map::~Map() {
     cudaSetDevice(device_);
-    pts_.release(); payload_.release(); next_.release(); counters_.release(); dir_tab_.release(); dir_lists_.release(); removed_.release(); ins_slots_.release();
+    pts_.release(); payload_.release(); next_.release(); counters_.release(); dir_tab_.release(); dir_lists_.release(); removed_.release(); ins_slots_.release(); dir_fix_.release();
     for (int k = 0; k < MAX_LEVELS; k++) ebox_[k].release();
     segid_.release(); segtab_[0].release(); segtab_[1].release(); bbox_.release();
     src_.release(); keys_in_.release(); keys_out_.release(); vals_in_.release(); vals_out_.release();
@@ -807,7 +856,7 @@ int Map::build_directory() {
         const size_t cells = (size_t)h_counters_[C_DIR_CELLS];
         if (h_counters_[C_DIR_ERROR] || cells * 10 > (size_t)v_.dir.cap * 6) { want_cap = std::max(want_cap * 2, cells * 5 / 2 + 16384); continue; }
         // lists: 27 listings per point + 25 % + 8 per cell (rounded to 4), plus room for the lists inserts will create
-        const size_t pool = (size_t)n_valid_ * 27 + (size_t)n_valid_ * 27 / 4 + cells * 12 + std::max<size_t>(dir_min_pool_, (size_t)HALO_NEW_CAP * 65536);
+        const size_t pool = (size_t)n_valid_ * 27 + (size_t)n_valid_ * 27 / 4 + cells * 12 + std::max<size_t>(dir_min_pool_, std::max<size_t>((size_t)HALO_NEW_CAP * 262144, (size_t)n_valid_ * 6));
         if (pool > 0x7ffffff0ull) { set_last_error("cell directory: list pool too large"); return FL_ERR_CAPACITY; }
         FL_CHECK(dir_lists_.reserve(sizeof(int) * pool));
         v_.dir.lists = dir_lists_.as<int>();
@@ -1011,7 +1060,11 @@ int Map::insert_device(const float4* d_pts, int n) {
     k_insert<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, n, counters_.as<int>(), ins_slots_.as<int>());
     if (v_.dir.cap) {
         k_halo_claim<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, ins_slots_.as<int>(), n, counters_.as<int>());
-        k_halo_append<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, ins_slots_.as<int>(), n, counters_.as<int>());
+        FL_CHECK(dir_fix_.reserve(sizeof(unsigned) * 65536));
+        FL_CUDA(cudaMemsetAsync(&counters_.as<int>()[C_NFIX], 0, sizeof(int), stream_));
+        k_halo_append<<<blocks_for((long long)n * 32, 256), 256, 0, stream_>>>(v_, d_pts, ins_slots_.as<int>(), n, counters_.as<int>(),
+                                                                                 dir_fix_.as<unsigned>(), 65536);
+        k_halo_fix<<<296, 256, 0, stream_>>>(v_, dir_fix_.as<unsigned>(), 65536, counters_.as<int>());
     }
     FL_CUDA(cudaGetLastError());
     FL_CUDA(cudaMemcpyAsync(h_counters_, counters_.ptr, sizeof(int) * C_COUNT, cudaMemcpyDeviceToHost, stream_));

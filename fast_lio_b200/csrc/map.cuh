@@ -33,8 +33,10 @@ namespace fl {
 // from the distance to the faces of that block; whatever it cannot prove -- nothing nearby, an over-full cell -- goes through the
 // warp-cooperative BVH walk below, so the result is always the exact answer of KD_TREE::Nearest_Search (ikd_Tree.cpp:426-461).
 // Every point is listed in the 27 cells around it (HBM is plentiful: ~130 bytes of directory per point).  Validity lives in the
-// slot's flag only: a deleted point keeps its listings and is skipped; a slot is re-used only by a point of the SAME cell, whose
-// 27 listings are then still right.
+// slot's flag only: a deleted point keeps its listings and is skipped.  A slot re-used by a later insert is listed again under
+// its new point's cells and keeps the old listings: a list may therefore name a slot twice, or name a slot whose point lies
+// outside the block -- both harmless (any live point is a legitimate candidate; the k-best list never takes a slot twice) and
+// packed away by the next re-list.
 constexpr int CELL_OFF = 1 << 20;                  // 21 bits per axis
 constexpr int CELL_CLAMP = (1 << 20) - 4;
 constexpr int HALO_MAX = 2048;                     // a cell whose block holds more points than this sends its queries to the BVH walk
@@ -70,7 +72,6 @@ struct MapView {
 // may revive it) / deleted by the down-sampling of Add_Points.  Deleted points keep their listing in the cell directory.
 constexpr int SLOT_FREE = 0, SLOT_VALID = 1, SLOT_BUSY = 2, SLOT_TOMB = 3, SLOT_TOMB_DS = 4;
 __device__ __forceinline__ bool slot_valid(const float4& p) { return __float_as_int(p.w) == SLOT_VALID; }
-
 // ----------------------------------------------------------------------------- k-best list
 // Lane j < K holds the j-th best (distance, slot); other lanes hold +inf.  Mirrors MANUAL_HEAP
 // + PointType_CMP (ikd_Tree.h:93-201) in effect: a candidate enters only if strictly closer
@@ -310,6 +311,11 @@ struct TBest {                       // k best of one thread, ascending; empty e
         for (int i = 0; i < KNN_K; i++) { d[i] = INFINITY; idx[i] = -1; }
     }
     __device__ __forceinline__ void insert(float nd, int nidx) {       // nd < d[K-1]; equal distances keep their arrival order
+        // a halo list may name a slot twice (a slot re-used by a later insert keeps its old listings): never keep it twice
+        bool dup = false;
+#pragma unroll
+        for (int i = 0; i < KNN_K; i++) dup |= idx[i] == nidx;
+        if (dup) return;
 #pragma unroll
         for (int i = KNN_K - 1; i > 0; i--) {
             const bool shift = nd < d[i - 1];

@@ -76,7 +76,7 @@ private:
     int n_valid_ = 0, n_tomb_ = 0, n_rebuilds_ = 0;
     bool built_ = false;
 
-    DeviceBuffer pts_, payload_, next_, counters_, dir_tab_, dir_lists_, removed_, ins_slots_;
+    DeviceBuffer pts_, payload_, next_, counters_, dir_tab_, dir_lists_, removed_, ins_slots_, dir_fix_;
     bool record_removed_ = false;
     int n_removed_ = 0;
     bool dir_enabled_ = true;

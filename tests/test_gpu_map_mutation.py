@@ -180,3 +180,37 @@ def test_acquire_removed_points_and_add_point_boxes(problems):
         qq = make_batch(rng, pr.map_pts, 200)
         r = bind.KdTree(pr.map_pts, "reference", downsample=0.5)
         assert np.array_equal(g2.Nearest_Search(qq, 5)[1], r.knn(qq, 5)[1])
+
+
+def test_directory_lists_grow_and_slots_are_reused():
+    """Inserts fill the halo lists of the cells they touch; a list that runs out of room is made anew from the map (k_halo_fix);
+    deleted points' slots are re-used by later inserts (their old listings stay behind).  The search must stay exact throughout."""
+    rng = np.random.default_rng(77)
+
+    def voxel_points(n, lo, hi):            # at most one point per 0.5 m voxel, like a down-sampled LiDAR map
+        c = np.unique(rng.integers(int(lo / 0.5), int(hi / 0.5), (n, 3)), axis=0)
+        p = np.zeros((len(c), 4), dtype=np.float32)
+        p[:, :3] = (c + rng.uniform(0.05, 0.45, c.shape)).astype(np.float32) * np.float32(0.5)
+        p[:, 3] = rng.uniform(1, 100, len(c)).astype(np.float32)
+        return p
+
+    base = voxel_points(3000, -20, 20)
+    g = api.KdTree(0, 0.5); g.Build(base)
+    cur = {tuple(r) for r in base}
+    for rep in range(12):
+        batch = voxel_points(2500, -12, 12)                                   # keeps hitting the same cells: their lists fill up
+        g.Add_Points(batch, False)
+        cur |= {tuple(r) for r in batch}
+        if rep % 3 == 2:                                                      # delete a slab, then refill it: slots get re-used
+            box = np.array([[-6.0, -30, -30, 0.0, 30, 30]], dtype=np.float32)
+            g.Delete_Point_Boxes(box)
+            cur = {r for r in cur if not (-6.0 <= r[0] < 0.0)}
+        pts = np.array(sorted(cur), dtype=np.float32)
+        assert g.validnum() == len(pts)
+        q = pts[rng.integers(0, len(pts), 300)] + rng.normal(0, 0.2, (300, 4)).astype(np.float32)
+        gp, gd, gc = g.Nearest_Search(q, 5)
+        for i in range(len(q)):
+            d = ((q[i, 0] - pts[:, 0]) ** 2 + (q[i, 1] - pts[:, 1]) ** 2) + (q[i, 2] - pts[:, 2]) ** 2
+            assert np.array_equal(gd[i], np.sort(d)[:5])
+    st = g.dir_stats()
+    assert st["enabled"] and st["walked"] < 300 * 12                          # and the directory is still answering most queries

@@ -72,7 +72,8 @@ out = {"workload": "avia_stream_24k", "n_gpus": world, "n_scans": n_scans, "poin
        "map": {"validnum": g.validnum(), "size": g.size(), **g.stats(), "directory": g.dir_stats()}}
 if world > 1:
     fl = g.flatten()
-    digest = torch.tensor([float(g.validnum()), float(fl[:, :3].astype(np.float64).sum()), float(np.abs(x).sum())], device="cuda", dtype=torch.float64)
+    fl = fl[np.lexsort((fl[:, 3], fl[:, 2], fl[:, 1], fl[:, 0]))]        # the replicas hold the same SET; slot order (hence flatten order) differs
+    digest = torch.tensor([float(g.validnum()), float(np.cumsum(fl[:, :3].astype(np.float64), axis=0)[-1].sum()), float(np.abs(x).sum())], device="cuda", dtype=torch.float64)
     ref = digest.clone(); dist.broadcast(ref, src=0)
     same = torch.tensor([1.0 if bool((digest == ref).all().item()) else 0.0], device="cuda")
     dist.all_reduce(same, op=dist.ReduceOp.MIN)

@@ -18,7 +18,7 @@ def _baseline():
         return json.load(f)
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_bench_n*.json"))))
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "profiles", "r[12]_bench_n*.json"))))
 def test_committed_bench_lines_follow_the_contract(path):
     with open(path) as f:
         lines = [l for l in f.read().splitlines() if l.strip()]

@@ -587,7 +587,7 @@ __device__ __noinline__ bool solve_gain_small_m(SolveShared& S, const FilterCtl*
 }
 
 template <int SOLVER, bool EXTR>
-__device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const ScanView& sc, PassLog* logs) {
+__device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const ScanView& sc, PassLog* logs, bool rows_local) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     constexpr int n = NDOF;
     STAMP(1);
@@ -623,7 +623,10 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
     constexpr int ne = EXTR ? 12 : 6;       // with extrinsic_est_en == false, columns 6..11 of h_x are zero
     if (!ok) {
         // fall through to the error exit below
-    } else if (effct < n) {
+    } else if (effct < n && rows_local) {
+        // the small-m form rebuilds the (< 23) Jacobian rows from this rank's points: only valid when all of them are here.  With
+        // the scan sharded over ranks the information form below is used instead -- the same gain by the matrix-inversion lemma,
+        // from the all-reduced sums alone
         ok = solve_gain_small_m(S, ctl, sc, extr, R);
     } else if constexpr (SOLVER == 0) {
         // -------------------------------------------------------------- information form exactly as the reference, esekfom.hpp:1782-1809
@@ -961,7 +964,7 @@ __global__ void __launch_bounds__(RESID_THREADS) k_residual(ScanView sc, FilterC
             return;
         }
     }
-    solve_finish<SOLVER, EXTR>(S, ctl, sc, logs);
+    solve_finish<SOLVER, EXTR>(S, ctl, sc, logs, mode == 0);
     mirror_result(ctl);
 }
 
@@ -989,7 +992,7 @@ __global__ void __launch_bounds__(RESID_THREADS) k_solve_only(FilterCtl* ctl, co
     solve_prepare<SOLVER>(S, ctl);
     if (threadIdx.x < NRED) S.red[threadIdx.x] = red_g[threadIdx.x];
     __syncthreads();
-    solve_finish<SOLVER, EXTR>(S, ctl, sc, logs);
+    solve_finish<SOLVER, EXTR>(S, ctl, sc, logs, false);        // multi-GPU: the rows live on several ranks
     mirror_result(ctl);
 }
 #undef STAMP

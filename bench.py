@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 A "step" is one whole update of one synthetic scan: every iEKF pass of
-update_iterated_dyn_share_modified, kNN included.  Workload at any N: BASELINE.json
+update_iterated_dyn_share_modified, kNN included -- ONE launch of the persistent kernel k_update.  Workload at any N: BASELINE.json
 configs[1] ("velodyne.yaml synthetic: 30k pts/scan vs 1M-pt map, 4 iEKF iters").
 
   value   scans/s with the scan, the map and the prior state resident in HBM
@@ -12,9 +12,11 @@ configs[1] ("velodyne.yaml synthetic: 30k pts/scan vs 1M-pt map, 4 iEKF iters").
           timed step with a 256 MB memset outside the events; max over ranks).
   e2e     scans/s through the public C-ABI call fl_filter_update() with HOST buffers:
           scan + state host->device and state device->host inside the timed region.
-  roofline  k_search (the dominant kernel), timed alone with CUDA events:
-          algorithmic bytes per launch (16 + 32*ceil(log2 N) + 32*k per point)
-          / launch time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  roofline  the kNN phase of one searching pass (the dominant part of the step), launched alone -- the persistent kernel
+          k_update in its search_only mode -- and timed with CUDA events: algorithmic bytes per launch
+          (16 + 32*ceil(log2 N) + 32*k per point) / launch time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  parity  the resident and the e2e state against the final state of the cpu_baseline leg (same scan, same prior);
+          above the north-star tolerance (1e-4 m / 1e-4 rad) the run exits with status 3.
   cpu_baseline  the reference's CPU path (its unmodified ikd-Tree from oracle/_ref + the
           restated h_share_model / esekf update) on this box's host cores, bounded sample.
 
@@ -357,7 +359,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "caller": "native loop over the public fl_filter_update (fl_filter_time_e2e)",
                     "via_python_ctypes_wrapper": 1.0 / e2e_py_s},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_update, search_only launch (the kNN phase of one searching pass: transform, cell-directory search + BVH walks, neighbours stored)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_launch, "launch_ms": ms_search, "launch_ms_l2_warm": ms_search_warm},
             "cpu_baseline": cpu,

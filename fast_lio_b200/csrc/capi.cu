@@ -271,7 +271,7 @@ int fl_filter_time_e2e(fl_filter_t* f, const float* body, int nq, const double* 
     return FL_OK;
 }
 
-// Device time of the dominant kernel alone: k_search (the kNN of the first pass of an update).
+// Device time of the dominant phase alone: the kNN of one searching pass (k_update's search_only launch; k_search_c / k_search on the legacy path).
 int fl_filter_time_search_pass(fl_filter_t* f, int reps, int flush_l2, float* ms_total) {
     FILTER_GUARD(f);
     if (reps < 1 || !ms_total) return FL_ERR_ARG;

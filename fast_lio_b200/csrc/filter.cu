@@ -801,7 +801,7 @@ __device__ __noinline__ void solve_finish(SolveShared& S, FilterCtl* ctl, const 
 
 // k_search_c -- the same search through the map's hashed cell directory: one LANE per scan point finds its cell's halo list (every
 // point of the 3x3x3 block of cells around it), scores it and proves its five neighbours exact; the few points it cannot prove
-// (nothing nearby, over-full cells) are walked through the BVH by the whole warp (knn_lanes, map.cuh).  Same neighbours, same
+// (nothing nearby, over-full cells) are pooled per block and walked through the BVH by its warps (knn_block, map.cuh).  Same neighbours, same
 // distances, bit for bit.
 __global__ void __maxnreg__(96) k_search_c(MapView m, ScanView sc, const FilterCtl* __restrict__ ctl) {
     __shared__ WalkPool pool;

@@ -279,13 +279,13 @@ __device__ __forceinline__ void box_query(const MapView& m, const float* bmin, c
 // ============================================================================= cell directory: search
 // One THREAD per query:
 //   1. one hashed look-up finds the entry of the query's cell;
-//   2. the points of its halo list (everything in the 3x3x3 block of cells around the query) are scored four at a time, loads
+//   2. the points of its halo list (everything in the 3x3x3 block of cells around the query) are scored eight at a time, loads
 //      first; the k best are kept in registers;
 //   3. every point OUTSIDE the block is at least g = (distance from the query to the block's faces) away, so the k best found
 //      are final when the k-th squared distance is strictly below g^2 (strict: the reference keeps the first of two
 //      equidistant candidates, ikd_Tree.cpp:1088) -- tests/cell_directory_model.py pins the rule on the CPU.
 // Anything else (no entry: nothing within a cell's width; fewer than k points; an over-full cell; coordinates beyond the key
-// range) is NOT answered here: knn_lanes() hands those queries to the warp-cooperative BVH walk (knn_query), one at a time.
+// range) is NOT answered here: knn_block() pools those queries per block and its warps walk them through the BVH (knn_query_from).
 // Squared distances use the same explicitly rounded float32 arithmetic as the BVH walk (sq_dist3): either route returns
 // bit-identical distances.  All margins shrink the proven radius, never the searched set.
 namespace fl {

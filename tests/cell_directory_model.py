@@ -1,5 +1,6 @@
-"""Round-2 groundwork (not product code): a numpy model of the hashed cell directory DESIGN.md §6c proposes for the
-map, to pin down the exact-k-NN termination rule before it is written as a kernel.
+"""Test infrastructure (not product code): numpy models of the map's hashed cell directory, pinning the
+exact-k-NN termination rule on the CPU.  CellDirectoryModel is the general ring search the rule was derived with;
+HaloRuleModel (below) restates what the kernel does -- ring 1 only, float32 cell arithmetic, safety margin.
 
 Points live in cubic cells of side `cell`; a query looks at its own cell and the rings of cells around it.  After ring
 r the region examined is the cube of (2r+1)^3 cells centred on the query's cell; every point OUTSIDE that cube is at
@@ -57,3 +58,45 @@ class CellDirectoryModel:
         idx = np.array([b[1] for b in best], dtype=np.int64)
         d2 = np.array([b[0] for b in best], dtype=np.float32)
         return idx, d2, r, probes
+
+
+class HaloRuleModel:
+    """The rule the product's thread search uses (fast_lio_b200/csrc/map.cuh, cell_knn), restated in float32 numpy with the
+    kernel's own arithmetic: points are filed by floor(fl(x * fl(1/cell))), a query sees the points filed in the 3x3x3 block of
+    cells around its own cell (its cell's halo list), and its k best are declared EXACT when the k-th squared distance is
+    strictly below g^2, g = (cell - marg) + the shrunk distance from the query to the nearest face of its own cell.  The float32
+    cell arithmetic can file a point one cell off when it sits within rounding of a face; marg = 4e-6 * (max|q| + 2 cell) must
+    cover that.  `knn` returns (indices, d2, proven); an unproven query is answered by the BVH walk in the product."""
+
+    def __init__(self, pts4, cell=1.0, marg_scale=1.0):
+        self.pts = np.asarray(pts4, dtype=np.float32).reshape(-1, 4)
+        self.cell = np.float32(cell)
+        self.inv = np.float32(1.0) / self.cell
+        self.marg_scale = np.float32(marg_scale)        # 1: the product's margin; 0: the naive rule (tests show it is wrong)
+        ijk = np.floor(self.pts[:, :3] * self.inv).astype(np.int64)
+        self.cells = {}
+        for i, c in enumerate(map(tuple, ijk)):
+            self.cells.setdefault(c, []).append(i)
+
+    def knn(self, q, k=5):
+        f = np.float32
+        q = np.asarray(q, dtype=np.float32)[:3]
+        c0 = np.floor(q * self.inv).astype(np.int64)
+        cand = []
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    cand += self.cells.get((c0[0] + dx, c0[1] + dy, c0[2] + dz), [])
+        if len(cand) < k:
+            return np.zeros(0, np.int64), np.zeros(0, np.float32), False
+        cand = np.array(sorted(cand), dtype=np.int64)
+        d = q[None, :] - self.pts[cand, :3]
+        d2 = ((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + d[:, 2] * d[:, 2]).astype(np.float32)
+        order = np.argsort(d2, kind="stable")[:k]
+        c = self.cell
+        marg = self.marg_scale * f(4e-6) * (f(np.abs(q).max()) + f(2) * c)
+        lo = np.maximum(q - c0.astype(np.float32) * c - marg, f(0))
+        hi = np.maximum((c0 + 1).astype(np.float32) * c - q - marg, f(0))
+        g = f(np.minimum(lo, hi).min() + (c - marg))
+        proven = bool(d2[order[-1]] < g * g)
+        return cand[order], d2[order], proven

@@ -395,17 +395,17 @@ def main():
     # Pin the OpenMP threads of the CPU reference path (must be in the environment before any OpenMP runtime starts) -- ONLY in a
     # single-process run: under torchrun the binding would put the main thread of EVERY rank on the same core (place 0), and the
     # ranks' host loops would time-share it (measured: 11 ms / 33 ms of wall clock per step at 4 / 8 ranks, device time unchanged).
+    if args.impl != "reference" and world != args.gpus and world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun (before the binding below enters the environment the ranks would inherit)
+        port = 29500 + (os.getpid() % 1000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
     if world == 1 or args.impl == "reference":
         os.environ.setdefault("OMP_PROC_BIND", "close")
         os.environ.setdefault("OMP_PLACES", "cores")
     if args.impl == "reference":
         return run_reference(args, rank)
-    if world != args.gpus and world == 1 and args.gpus > 1:
-        # convenience: re-launch under torchrun
-        port = 29500 + (os.getpid() % 1000)
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
-        return subprocess.call(cmd)
     return run_ours(args, rank, world, local_rank)
 
 
